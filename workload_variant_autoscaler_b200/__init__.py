@@ -1,0 +1,3 @@
+"""B200-native implementation of the WVA optimizer hot path."""
+from ._abi import ACC_NONE, ACC_UNKNOWN, Allocs  # noqa: F401
+from .fleet import Fleet, Grid, config2_grid, synth_fleet  # noqa: F401
