@@ -1,0 +1,1036 @@
+// wva_b200.cu — host engine + C ABI (include/wva_b200.h) over the sm_100a kernels.
+//
+// Host-side mirror of pkg/core.System / pkg/manager.Manager for the hot path: the fleet
+// is packed once into a single device arena (one H2D copy), derived work lists
+// (candidates ordered by queue size, shared service-rate tables) are cached on the
+// handle, every call enqueues its kernels on the handle's stream and ends with one D2H
+// copy of the result block.  There is no CPU compute fallback: without a CUDA device
+// wva_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/wva_b200.h"
+#include "wva_kernels.cuh"
+
+using namespace wva;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Host copy of the fleet columns (the caller's pointers are never retained).
+struct HostFleet {
+    int A = 0, T = 0, M = 0, S = 0;
+    std::vector<float> acc_cost;
+    std::vector<int32_t> acc_mult, acc_type, type_capacity;
+    std::vector<uint8_t> perf_present;
+    std::vector<float> perf_alpha, perf_beta, perf_gamma, perf_delta;
+    std::vector<int32_t> perf_acc_count, perf_max_batch, perf_at_tokens;
+    std::vector<int32_t> srv_model, srv_priority;
+    std::vector<uint8_t> srv_has_target;
+    std::vector<float> srv_slo_itl, srv_slo_ttft, srv_slo_tps;
+    std::vector<uint8_t> srv_keep_acc;
+    std::vector<int32_t> srv_min_replicas, srv_max_batch;
+    std::vector<float> srv_arrival_rpm;
+    std::vector<int32_t> srv_in_tokens, srv_out_tokens, srv_cur_acc, srv_cur_replicas;
+    std::vector<float> srv_cur_cost;
+    bool unlimited = true, delayed_best_effort = false;
+    int saturation_policy = 0;
+    wva_tunables tun{10, 0.1f};
+
+    // gates of CreateAllocation + candidate rule (mirrors pair_class on the device)
+    int pair_class(int s, int a, bool honour_keep) const {
+        if (honour_keep && srv_keep_acc[s] && srv_cur_acc[s] != WVA_ACC_NONE && srv_cur_acc[s] != a) return 0;
+        if (srv_arrival_rpm[s] < 0.0f || srv_in_tokens[s] < 0 || srv_out_tokens[s] < 0) return 0;
+        const int m = srv_model[s];
+        if (m < 0 || m >= M) return 0;
+        if (!perf_present[(size_t)m * A + a]) return 0;
+        if (!srv_has_target[s]) return 0;
+        if (srv_arrival_rpm[s] == 0.0f || srv_out_tokens[s] == 0) return PAIR_ZERO;
+        return PAIR_LOAD;
+    }
+    // batch size of a candidate: pkg/core/allocation.go:77-87
+    int pair_batch(int s, int a) const {
+        if (srv_max_batch[s] > 0) return srv_max_batch[s];
+        const size_t k = (size_t)srv_model[s] * A + a;
+        const long long t = (long long)perf_max_batch[k] * (long long)perf_at_tokens[k] / srv_out_tokens[s];
+        return (int)std::max<long long>(t, 1);
+    }
+};
+
+struct Column {
+    size_t off, bytes;
+};
+
+}  // namespace
+
+struct wva_handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    float last_kernel_ms = 0.f, last_device_ms = 0.f;
+
+    // resident fleet
+    bool resident = false;
+    HostFleet hf;
+    DevBuf arena;
+    PinBuf stage;
+    DevFleet df{};
+    Column col_rate{}, col_in{}, col_out{};
+    uint64_t epoch_tokens = 0;  // bumped when service-rate tables become stale
+
+    // size path caches
+    uint64_t size_epoch = ~0ull;
+    std::vector<int> cand_pair, cand_N;
+    std::vector<long long> group_off;
+    int size_Nmax = 0;
+    DevBuf d_cand_pair, d_cand_N, d_group_off, d_ltab;
+    // grid path caches
+    uint64_t grid_epoch = ~0ull;
+    std::vector<int> grid_batch, grid_replicas;
+    int grid_Bmax = 0, grid_n_tab = 0;
+    DevBuf d_grid_lists, d_pair_tab, d_tab_pair, d_tab_off, d_tab_len, d_tab, d_partials;
+    // shared
+    DevBuf d_cand_block, d_win_block, d_ctrl, d_fb_list, d_fb_cands, d_scratch, d_cells, d_sweep;
+    PinBuf out_stage;
+
+    int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+        err = what;
+        if (e != cudaSuccess) {
+            err += ": ";
+            err += cudaGetErrorString(e);
+        }
+        return code;
+    }
+};
+
+#define CK(call)                                                              \
+    do {                                                                      \
+        cudaError_t _e = (call);                                              \
+        if (_e != cudaSuccess) return h->fail(WVA_ERR_CUDA, #call, _e);       \
+    } while (0)
+
+namespace {
+
+// control block on the device: a handful of ints
+enum { CTRL_COUNTER = 0, CTRL_FB_COUNT = 1, CTRL_FB_STATUS = 2, CTRL_INTS = 8 };
+
+// ---- SoA result blocks -------------------------------------------------------
+struct Block {
+    size_t off_feasible, off_acc, off_replicas, off_batch, off_cost, off_value, off_itl, off_ttft, off_rho, off_rate;
+    size_t bytes;
+    size_t n;
+};
+Block block_layout(size_t n) {
+    Block b;
+    size_t o = 0;
+    b.n = n;
+    b.off_feasible = o; o = align_up(o + n, 16);
+    b.off_acc = o; o = align_up(o + 4 * n, 16);
+    b.off_replicas = o; o = align_up(o + 4 * n, 16);
+    b.off_batch = o; o = align_up(o + 4 * n, 16);
+    b.off_cost = o; o = align_up(o + 4 * n, 16);
+    b.off_value = o; o = align_up(o + 4 * n, 16);
+    b.off_itl = o; o = align_up(o + 4 * n, 16);
+    b.off_ttft = o; o = align_up(o + 4 * n, 16);
+    b.off_rho = o; o = align_up(o + 4 * n, 16);
+    b.off_rate = o; o = align_up(o + 4 * n, 16);
+    b.bytes = o;
+    return b;
+}
+AllocCols block_cols(void* base, const Block& b) {
+    char* p = (char*)base;
+    AllocCols c;
+    c.feasible = (uint8_t*)(p + b.off_feasible);
+    c.acc = (int*)(p + b.off_acc);
+    c.replicas = (int*)(p + b.off_replicas);
+    c.batch = (int*)(p + b.off_batch);
+    c.cost = (float*)(p + b.off_cost);
+    c.value = (float*)(p + b.off_value);
+    c.itl = (float*)(p + b.off_itl);
+    c.ttft = (float*)(p + b.off_ttft);
+    c.rho = (float*)(p + b.off_rho);
+    c.max_rate = (float*)(p + b.off_rate);
+    return c;
+}
+void scatter_block(const void* host_block, const Block& b, const wva_allocs* out) {
+    if (!out) return;
+    const char* p = (const char*)host_block;
+    const size_t n = b.n;
+    if (out->feasible) memcpy(out->feasible, p + b.off_feasible, n);
+    if (out->acc) memcpy(out->acc, p + b.off_acc, 4 * n);
+    if (out->replicas) memcpy(out->replicas, p + b.off_replicas, 4 * n);
+    if (out->batch) memcpy(out->batch, p + b.off_batch, 4 * n);
+    if (out->cost) memcpy(out->cost, p + b.off_cost, 4 * n);
+    if (out->value) memcpy(out->value, p + b.off_value, 4 * n);
+    if (out->itl) memcpy(out->itl, p + b.off_itl, 4 * n);
+    if (out->ttft) memcpy(out->ttft, p + b.off_ttft, 4 * n);
+    if (out->rho) memcpy(out->rho, p + b.off_rho, 4 * n);
+    if (out->max_rate) memcpy(out->max_rate, p + b.off_rate, 4 * n);
+}
+AllocCols cols_from_abi(const wva_allocs* a) {
+    AllocCols c{};
+    if (!a) return c;
+    c.feasible = a->feasible; c.acc = a->acc; c.replicas = a->replicas; c.batch = a->batch;
+    c.cost = a->cost; c.value = a->value; c.itl = a->itl; c.ttft = a->ttft; c.rho = a->rho;
+    c.max_rate = a->max_rate;
+    return c;
+}
+
+// ---- fleet validation + upload ----------------------------------------------
+int validate_fleet(wva_handle* h, const wva_fleet* f) {
+    if (!f) return h->fail(WVA_ERR_BAD_ARG, "fleet is NULL");
+    if (f->n_acc < 0 || f->n_types < 0 || f->n_models < 0 || f->n_servers < 0)
+        return h->fail(WVA_ERR_BAD_ARG, "negative size in fleet");
+    const bool need_a = f->n_acc > 0, need_t = f->n_types > 0, need_ma = f->n_models > 0 && f->n_acc > 0,
+               need_s = f->n_servers > 0;
+    if (need_a && (!f->acc_cost || !f->acc_multiplicity || !f->acc_type))
+        return h->fail(WVA_ERR_BAD_ARG, "NULL accelerator column");
+    if (need_t && !f->type_capacity) return h->fail(WVA_ERR_BAD_ARG, "NULL capacity column");
+    if (need_ma && (!f->perf_present || !f->perf_alpha || !f->perf_beta || !f->perf_gamma || !f->perf_delta ||
+                    !f->perf_acc_count || !f->perf_max_batch || !f->perf_at_tokens))
+        return h->fail(WVA_ERR_BAD_ARG, "NULL perf column");
+    if (need_s && (!f->srv_model || !f->srv_priority || !f->srv_has_target || !f->srv_slo_itl || !f->srv_slo_ttft ||
+                   !f->srv_slo_tps || !f->srv_keep_acc || !f->srv_min_replicas || !f->srv_max_batch ||
+                   !f->srv_arrival_rpm || !f->srv_in_tokens || !f->srv_out_tokens || !f->srv_cur_acc ||
+                   !f->srv_cur_replicas || !f->srv_cur_cost))
+        return h->fail(WVA_ERR_BAD_ARG, "NULL server column");
+    for (int a = 0; a < f->n_acc; ++a)
+        if (f->n_types > 0 && (f->acc_type[a] < 0 || f->acc_type[a] >= f->n_types))
+            return h->fail(WVA_ERR_BAD_ARG, "accelerator type id out of range");
+    if (f->tun.max_queue_to_batch_ratio < 0) return h->fail(WVA_ERR_BAD_ARG, "negative queue ratio");
+    return WVA_OK;
+}
+
+template <class T>
+void copy_col(std::vector<T>& dst, const T* src, size_t n) {
+    dst.assign(src, src + n);
+}
+
+template <class T>
+Column place(std::vector<std::pair<Column, const void*>>& plan, size_t& off, const std::vector<T>& v) {
+    Column c{off, v.size() * sizeof(T)};
+    plan.push_back({c, v.data()});
+    off = align_up(off + std::max<size_t>(c.bytes, 1));
+    return c;
+}
+
+int upload_fleet(wva_handle* h, const wva_fleet* f) {
+    int rc = validate_fleet(h, f);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));  // the pinned stage may still feed an earlier async copy
+    HostFleet& hf = h->hf;
+    const size_t A = f->n_acc, T = f->n_types, M = f->n_models, S = f->n_servers;
+    hf.A = (int)A; hf.T = (int)T; hf.M = (int)M; hf.S = (int)S;
+    copy_col(hf.acc_cost, f->acc_cost, A);
+    copy_col(hf.acc_mult, f->acc_multiplicity, A);
+    copy_col(hf.acc_type, f->acc_type, A);
+    copy_col(hf.type_capacity, f->type_capacity, T);
+    copy_col(hf.perf_present, f->perf_present, M * A);
+    copy_col(hf.perf_alpha, f->perf_alpha, M * A);
+    copy_col(hf.perf_beta, f->perf_beta, M * A);
+    copy_col(hf.perf_gamma, f->perf_gamma, M * A);
+    copy_col(hf.perf_delta, f->perf_delta, M * A);
+    copy_col(hf.perf_acc_count, f->perf_acc_count, M * A);
+    copy_col(hf.perf_max_batch, f->perf_max_batch, M * A);
+    copy_col(hf.perf_at_tokens, f->perf_at_tokens, M * A);
+    copy_col(hf.srv_model, f->srv_model, S);
+    copy_col(hf.srv_priority, f->srv_priority, S);
+    copy_col(hf.srv_has_target, f->srv_has_target, S);
+    copy_col(hf.srv_slo_itl, f->srv_slo_itl, S);
+    copy_col(hf.srv_slo_ttft, f->srv_slo_ttft, S);
+    copy_col(hf.srv_slo_tps, f->srv_slo_tps, S);
+    copy_col(hf.srv_keep_acc, f->srv_keep_acc, S);
+    copy_col(hf.srv_min_replicas, f->srv_min_replicas, S);
+    copy_col(hf.srv_max_batch, f->srv_max_batch, S);
+    copy_col(hf.srv_arrival_rpm, f->srv_arrival_rpm, S);
+    copy_col(hf.srv_in_tokens, f->srv_in_tokens, S);
+    copy_col(hf.srv_out_tokens, f->srv_out_tokens, S);
+    copy_col(hf.srv_cur_acc, f->srv_cur_acc, S);
+    copy_col(hf.srv_cur_replicas, f->srv_cur_replicas, S);
+    copy_col(hf.srv_cur_cost, f->srv_cur_cost, S);
+    hf.unlimited = f->unlimited != 0;
+    hf.delayed_best_effort = f->delayed_best_effort != 0;
+    hf.saturation_policy = f->saturation_policy;
+    hf.tun = f->tun;
+
+    // one arena, one H2D copy; the three load columns are adjacent so that
+    // wva_update_load moves a single contiguous range
+    std::vector<std::pair<Column, const void*>> plan;
+    size_t off = 0;
+    Column c_rate = place(plan, off, hf.srv_arrival_rpm);
+    Column c_in = place(plan, off, hf.srv_in_tokens);
+    Column c_out = place(plan, off, hf.srv_out_tokens);
+    Column c_acc_cost = place(plan, off, hf.acc_cost);
+    Column c_acc_mult = place(plan, off, hf.acc_mult);
+    Column c_acc_type = place(plan, off, hf.acc_type);
+    Column c_cap = place(plan, off, hf.type_capacity);
+    Column c_pp = place(plan, off, hf.perf_present);
+    Column c_pa = place(plan, off, hf.perf_alpha);
+    Column c_pb = place(plan, off, hf.perf_beta);
+    Column c_pg = place(plan, off, hf.perf_gamma);
+    Column c_pd = place(plan, off, hf.perf_delta);
+    Column c_pc = place(plan, off, hf.perf_acc_count);
+    Column c_pm = place(plan, off, hf.perf_max_batch);
+    Column c_pt = place(plan, off, hf.perf_at_tokens);
+    Column c_sm = place(plan, off, hf.srv_model);
+    Column c_sp = place(plan, off, hf.srv_priority);
+    Column c_st = place(plan, off, hf.srv_has_target);
+    Column c_si = place(plan, off, hf.srv_slo_itl);
+    Column c_sf = place(plan, off, hf.srv_slo_ttft);
+    Column c_ss = place(plan, off, hf.srv_slo_tps);
+    Column c_sk = place(plan, off, hf.srv_keep_acc);
+    Column c_sn = place(plan, off, hf.srv_min_replicas);
+    Column c_sb = place(plan, off, hf.srv_max_batch);
+    Column c_ca = place(plan, off, hf.srv_cur_acc);
+    Column c_cr = place(plan, off, hf.srv_cur_replicas);
+    Column c_cc = place(plan, off, hf.srv_cur_cost);
+    const size_t total = off;
+    CK(h->arena.ensure(total));
+    CK(h->stage.ensure(total));
+    for (auto& pr : plan)
+        if (pr.first.bytes) memcpy((char*)h->stage.p + pr.first.off, pr.second, pr.first.bytes);
+    CK(cudaMemcpyAsync(h->arena.p, h->stage.p, total, cudaMemcpyHostToDevice, h->stream));
+
+    char* d = (char*)h->arena.p;
+    DevFleet& df = h->df;
+    df.A = hf.A; df.T = hf.T; df.M = hf.M; df.S = hf.S;
+    df.acc_cost = (const float*)(d + c_acc_cost.off);
+    df.acc_mult = (const int*)(d + c_acc_mult.off);
+    df.acc_type = (const int*)(d + c_acc_type.off);
+    df.type_capacity = (const int*)(d + c_cap.off);
+    df.perf_present = (const uint8_t*)(d + c_pp.off);
+    df.perf_alpha = (const float*)(d + c_pa.off);
+    df.perf_beta = (const float*)(d + c_pb.off);
+    df.perf_gamma = (const float*)(d + c_pg.off);
+    df.perf_delta = (const float*)(d + c_pd.off);
+    df.perf_acc_count = (const int*)(d + c_pc.off);
+    df.perf_max_batch = (const int*)(d + c_pm.off);
+    df.perf_at_tokens = (const int*)(d + c_pt.off);
+    df.srv_model = (const int*)(d + c_sm.off);
+    df.srv_priority = (const int*)(d + c_sp.off);
+    df.srv_has_target = (const uint8_t*)(d + c_st.off);
+    df.srv_slo_itl = (const float*)(d + c_si.off);
+    df.srv_slo_ttft = (const float*)(d + c_sf.off);
+    df.srv_slo_tps = (const float*)(d + c_ss.off);
+    df.srv_keep_acc = (const uint8_t*)(d + c_sk.off);
+    df.srv_min_replicas = (const int*)(d + c_sn.off);
+    df.srv_max_batch = (const int*)(d + c_sb.off);
+    df.srv_arrival_rpm = (const float*)(d + c_rate.off);
+    df.srv_in_tokens = (const int*)(d + c_in.off);
+    df.srv_out_tokens = (const int*)(d + c_out.off);
+    df.srv_cur_acc = (const int*)(d + c_ca.off);
+    df.srv_cur_replicas = (const int*)(d + c_cr.off);
+    df.srv_cur_cost = (const float*)(d + c_cc.off);
+    df.ratio = hf.tun.max_queue_to_batch_ratio;
+    df.penalty = hf.tun.accel_penalty_factor;
+    h->col_rate = c_rate; h->col_in = c_in; h->col_out = c_out;
+    h->resident = true;
+    h->epoch_tokens++;
+    return WVA_OK;
+}
+
+int ensure_ctrl(wva_handle* h) {
+    CK(h->d_ctrl.ensure(CTRL_INTS * sizeof(int)));
+    CK(cudaMemsetAsync(h->d_ctrl.p, 0, CTRL_INTS * sizeof(int), h->stream));
+    return WVA_OK;
+}
+
+// Scratch for the stored-vector fallback kernels: a fixed number of slots.
+constexpr int kFbBlocks = 2, kFbThreads = 64, kFbSlots = kFbBlocks * kFbThreads;
+int ensure_scratch(wva_handle* h, int Nmax, int ratio, size_t* slot_doubles, int* Kmax) {
+    *Kmax = Nmax + Nmax * ratio;
+    *slot_doubles = (size_t)*Kmax + 1 + ((size_t)Nmax + 1) / 2 + 1;
+    CK(h->d_scratch.ensure(*slot_doubles * sizeof(double) * kFbSlots));
+    return WVA_OK;
+}
+
+// ---- size path (K1) ---------------------------------------------------------
+int prepare_size(wva_handle* h) {
+    if (h->size_epoch == h->epoch_tokens) return WVA_OK;
+    const HostFleet& hf = h->hf;
+    const int A = hf.A, S = hf.S;
+    std::vector<int> pairs;
+    std::vector<int> Ns((size_t)S * A, 0);
+    for (int s = 0; s < S; ++s)
+        for (int a = 0; a < A; ++a)
+            if (hf.pair_class(s, a, true) == PAIR_LOAD) {
+                const int N = hf.pair_batch(s, a);
+                if (N > (1 << 20)) return h->fail(WVA_ERR_UNSUPPORTED, "batch size above 2^20");
+                Ns[(size_t)s * A + a] = N;
+                pairs.push_back(s * A + a);
+            }
+    std::stable_sort(pairs.begin(), pairs.end(), [&](int x, int y) { return Ns[x] > Ns[y]; });
+    const int n = (int)pairs.size();
+    h->cand_pair = pairs;
+    h->cand_N.resize(n);
+    for (int j = 0; j < n; ++j) h->cand_N[j] = Ns[pairs[j]];
+    const int n_groups = (n + 31) / 32;
+    h->group_off.assign(n_groups + 1, 0);
+    for (int g = 0; g < n_groups; ++g) h->group_off[g + 1] = h->group_off[g] + (long long)h->cand_N[g * 32] * 32;
+    h->size_Nmax = n ? h->cand_N[0] : 1;
+    if (n) {
+        CK(h->d_cand_pair.ensure(sizeof(int) * n));
+        CK(h->d_cand_N.ensure(sizeof(int) * n));
+        CK(h->d_group_off.ensure(sizeof(long long) * (n_groups + 1)));
+        CK(h->d_ltab.ensure(sizeof(float) * (size_t)h->group_off[n_groups]));
+        CK(cudaMemcpyAsync(h->d_cand_pair.p, h->cand_pair.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_cand_N.p, h->cand_N.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_group_off.p, h->group_off.data(), sizeof(long long) * (n_groups + 1),
+                           cudaMemcpyHostToDevice, h->stream));
+        // the host vectors above stay alive until the next prepare_size, and every
+        // entry point synchronises before returning, so pageable sources are safe here
+        build_lane_tables<<<n_groups, 256, 0, h->stream>>>(h->df, (const int*)h->d_cand_pair.p,
+                                                           (const int*)h->d_cand_N.p, n,
+                                                           (const long long*)h->d_group_off.p, (float*)h->d_ltab.p);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    h->size_epoch = h->epoch_tokens;
+    return WVA_OK;
+}
+
+// Enqueue analyze (+ unlimited solve). cand/winner columns are device pointers.
+int enqueue_size(wva_handle* h, const AllocCols& cand, const AllocCols* winners) {
+    int rc = prepare_size(h);
+    if (rc) return rc;
+    rc = ensure_ctrl(h);
+    if (rc) return rc;
+    const HostFleet& hf = h->hf;
+    const int n_pairs = hf.S * hf.A;
+    const int n = (int)h->cand_pair.size();
+    if (n_pairs > 0) {
+        trivial_kernel<<<(n_pairs + 255) / 256, 256, 0, h->stream>>>(h->df, cand);
+        h->launches++;
+    }
+    SizeArgs g{};
+    g.f = h->df;
+    g.cand_pair = (const int*)h->d_cand_pair.p;
+    g.cand_N = (const int*)h->d_cand_N.p;
+    g.n_cand = n;
+    g.ltab = (const float*)h->d_ltab.p;
+    g.group_off = (const long long*)h->d_group_off.p;
+    g.cand = cand;
+    g.fb_count = (int*)h->d_ctrl.p + CTRL_FB_COUNT;
+    CK(h->d_fb_list.ensure(sizeof(int) * std::max(n, 1)));
+    g.fb_list = (int*)h->d_fb_list.p;
+    g.fb_cap = std::max(n, 1);
+    CK(cudaEventRecord(h->ev_k0, h->stream));
+    if (n > 0) {
+        size_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(g);
+        h->launches++;
+    }
+    CK(cudaEventRecord(h->ev_k1, h->stream));
+    if (n > 0) {
+        size_t slot_doubles;
+        int Kmax;
+        rc = ensure_scratch(h, h->size_Nmax, hf.tun.max_queue_to_batch_ratio, &slot_doubles, &Kmax);
+        if (rc) return rc;
+        size_fallback<<<kFbBlocks, kFbThreads, 0, h->stream>>>(g, (double*)h->d_scratch.p, slot_doubles, Kmax,
+                                                               (int*)h->d_ctrl.p + CTRL_FB_STATUS);
+        h->launches++;
+    }
+    if (winners && hf.S > 0) {
+        unlimited_kernel<<<(hf.S + 127) / 128, 128, 0, h->stream>>>(h->df, cand, *winners);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    return WVA_OK;
+}
+
+int finish_timing(wva_handle* h) {
+    CK(cudaEventRecord(h->ev_d1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->last_kernel_ms, h->ev_k0, h->ev_k1);
+    cudaEventElapsedTime(&h->last_device_ms, h->ev_d0, h->ev_d1);
+    return WVA_OK;
+}
+
+int check_fallback_status(wva_handle* h, const int* ctrl_host, long long cap) {
+    if (ctrl_host[CTRL_FB_STATUS] != 0)
+        return h->fail(WVA_ERR_UNSUPPORTED, "input outside the supported numeric domain (rescale loop does not terminate)");
+    if ((long long)ctrl_host[CTRL_FB_COUNT] > cap)
+        return h->fail(WVA_ERR_UNSUPPORTED, "too many cells need the stored-vector fallback");
+    return WVA_OK;
+}
+
+// resident analyze/solve with host outputs
+int run_size_host(wva_handle* h, wva_allocs* candidates, wva_allocs* winners) {
+    if (!h->resident) return h->fail(WVA_ERR_STATE, "no resident fleet (call wva_upload first)");
+    const HostFleet& hf = h->hf;
+    const size_t n_pairs = (size_t)hf.S * hf.A;
+    const Block bc = block_layout(n_pairs), bw = block_layout(hf.S);
+    CK(h->d_cand_block.ensure(bc.bytes + 16));
+    CK(h->d_win_block.ensure(bw.bytes + 16));
+    const AllocCols dc = block_cols(h->d_cand_block.p, bc), dw = block_cols(h->d_win_block.p, bw);
+    CK(cudaEventRecord(h->ev_d0, h->stream));
+    int rc = enqueue_size(h, dc, winners ? &dw : nullptr);
+    if (rc) return rc;
+    const size_t stage_bytes = align_up(bc.bytes) + align_up(bw.bytes) + 256;
+    CK(h->out_stage.ensure(stage_bytes));
+    char* hs = (char*)h->out_stage.p;
+    if (candidates && bc.bytes) CK(cudaMemcpyAsync(hs, h->d_cand_block.p, bc.bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (winners && bw.bytes)
+        CK(cudaMemcpyAsync(hs + align_up(bc.bytes), h->d_win_block.p, bw.bytes, cudaMemcpyDeviceToHost, h->stream));
+    int* ctrl_host = (int*)(hs + align_up(bc.bytes) + align_up(bw.bytes));
+    CK(cudaMemcpyAsync(ctrl_host, h->d_ctrl.p, CTRL_INTS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    rc = finish_timing(h);
+    if (rc) return rc;
+    rc = check_fallback_status(h, ctrl_host, (long long)h->cand_pair.size() + 1);
+    if (rc) return rc;
+    scatter_block(hs, bc, candidates);
+    scatter_block(hs + align_up(bc.bytes), bw, winners);
+    return WVA_OK;
+}
+
+// ---- grid path (K2 + K3) ----------------------------------------------------
+int validate_grid(wva_handle* h, const wva_grid* g) {
+    if (!g) return h->fail(WVA_ERR_BAD_ARG, "grid is NULL");
+    if (g->n_batch < 0 || g->n_replicas < 0) return h->fail(WVA_ERR_BAD_ARG, "negative grid size");
+    if ((g->n_batch > 0 && !g->batch) || (g->n_replicas > 0 && !g->replicas))
+        return h->fail(WVA_ERR_BAD_ARG, "NULL grid column");
+    for (int i = 0; i < g->n_batch; ++i)
+        if (g->batch[i] < 1 || g->batch[i] > (1 << 20)) return h->fail(WVA_ERR_BAD_ARG, "batch size out of range");
+    for (int i = 0; i < g->n_replicas; ++i)
+        if (g->replicas[i] < 1) return h->fail(WVA_ERR_BAD_ARG, "replica count out of range");
+    return WVA_OK;
+}
+
+struct GridPlan {
+    GridArgs args;
+    size_t n_cells;
+    int n_tab;
+    int Bmax;
+};
+
+int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
+    const HostFleet& hf = h->hf;
+    const int A = hf.A, S = hf.S, B = grid->n_batch, R = grid->n_replicas;
+    const bool same_grid = h->grid_epoch == h->epoch_tokens && (int)h->grid_batch.size() == B &&
+                           (int)h->grid_replicas.size() == R &&
+                           std::equal(h->grid_batch.begin(), h->grid_batch.end(), grid->batch) &&
+                           std::equal(h->grid_replicas.begin(), h->grid_replicas.end(), grid->replicas);
+    const int n_pairs = S * A;
+    int Bmax = 1;
+    for (int i = 0; i < B; ++i) Bmax = std::max(Bmax, grid->batch[i]);
+    // device lists: batch[B], order[B], replicas[R]
+    const size_t lists_bytes = sizeof(int) * (size_t)(2 * B + R + 1);
+    CK(h->d_grid_lists.ensure(lists_bytes));
+    CK(h->d_pair_tab.ensure(sizeof(long long) * std::max(n_pairs, 1)));
+    // pageable sources: cudaMemcpyAsync has consumed them by the time it returns
+    std::vector<int> lists, tab_pair, tab_len;
+    std::vector<long long> pair_tab, tab_off;
+    if (!same_grid) {
+        h->grid_batch.assign(grid->batch, grid->batch + B);
+        h->grid_replicas.assign(grid->replicas, grid->replicas + R);
+        lists.resize(2 * B + R + 1);
+        std::vector<int> order(B);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return grid->batch[x] > grid->batch[y]; });
+        for (int i = 0; i < B; ++i) {
+            lists[i] = grid->batch[i];
+            lists[B + i] = order[i];
+        }
+        for (int i = 0; i < R; ++i) lists[2 * B + i] = grid->replicas[i];
+        if (2 * B + R > 0)
+            CK(cudaMemcpyAsync(h->d_grid_lists.p, lists.data(), sizeof(int) * (size_t)(2 * B + R), cudaMemcpyHostToDevice,
+                               h->stream));
+        // shared service-rate tables for every pair that carries load
+        pair_tab.assign(std::max(n_pairs, 1), -1);
+        tab_pair.clear();
+        tab_off.clear();
+        tab_len.clear();
+        long long off = 0;
+        for (int s = 0; s < S; ++s)
+            for (int a = 0; a < A; ++a)
+                if (hf.pair_class(s, a, true) == PAIR_LOAD && hf.srv_out_tokens[s] >= 1) {
+                    pair_tab[(size_t)s * A + a] = off;
+                    tab_pair.push_back(s * A + a);
+                    tab_off.push_back(off);
+                    tab_len.push_back(Bmax);
+                    off += Bmax;
+                }
+        const int n_tab = (int)tab_pair.size();
+        CK(cudaMemcpyAsync(h->d_pair_tab.p, pair_tab.data(), sizeof(long long) * std::max(n_pairs, 1),
+                           cudaMemcpyHostToDevice, h->stream));
+        if (n_tab) {
+            CK(h->d_tab_pair.ensure(sizeof(int) * n_tab));
+            CK(h->d_tab_off.ensure(sizeof(long long) * n_tab));
+            CK(h->d_tab_len.ensure(sizeof(int) * n_tab));
+            CK(h->d_tab.ensure(sizeof(double) * 3 * (size_t)off));
+            CK(cudaMemcpyAsync(h->d_tab_pair.p, tab_pair.data(), sizeof(int) * n_tab, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->d_tab_off.p, tab_off.data(), sizeof(long long) * n_tab, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->d_tab_len.p, tab_len.data(), sizeof(int) * n_tab, cudaMemcpyHostToDevice, h->stream));
+        }
+        h->grid_n_tab = n_tab;
+        h->grid_Bmax = Bmax;
+        h->grid_epoch = h->epoch_tokens;
+    }
+    // the tables are rebuilt on every call (only the host-side work lists are cached):
+    // they are part of the evaluation, not an input
+    if (h->grid_n_tab) {
+        build_pair_tables<<<h->grid_n_tab, 128, 0, h->stream>>>(h->df, (const int*)h->d_tab_pair.p,
+                                                                (const long long*)h->d_tab_off.p,
+                                                                (const int*)h->d_tab_len.p, h->grid_n_tab,
+                                                                (double*)h->d_tab.p);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    GridArgs& g = plan->args;
+    g = GridArgs{};
+    g.f = h->df;
+    g.batch = (const int*)h->d_grid_lists.p;
+    g.batch_order = g.batch + B;
+    g.replicas = g.batch + 2 * B;
+    g.B = B;
+    g.R = R;
+    g.tab = (const double*)h->d_tab.p;
+    g.pair_tab_off = (const long long*)h->d_pair_tab.p;
+    g.n_chunks = (A * R + 31) / 32;
+    const size_t n_part = (size_t)S * B * std::max(g.n_chunks, 1);
+    CK(h->d_partials.ensure(sizeof(Cand) * std::max<size_t>(n_part, 1)));
+    g.partials = (Cand*)h->d_partials.p;
+    g.counter = (unsigned*)h->d_ctrl.p + CTRL_COUNTER;
+    const unsigned long long n_items = (unsigned long long)S * B * g.n_chunks;
+    if (n_items > 0xfffffff0ull) return h->fail(WVA_ERR_UNSUPPORTED, "grid too large for one call");
+    g.n_items = (unsigned)n_items;
+    plan->n_cells = (size_t)S * A * B * R;
+    g.fb_count = (int*)h->d_ctrl.p + CTRL_FB_COUNT;
+    g.fb_cap = (int)std::min<size_t>(std::max<size_t>(plan->n_cells, 1), (size_t)1 << 22);
+    CK(h->d_fb_list.ensure(sizeof(long long) * g.fb_cap));
+    CK(h->d_fb_cands.ensure(sizeof(Cand) * g.fb_cap));
+    g.fb_cells = (long long*)h->d_fb_list.p;
+    plan->Bmax = Bmax;
+    return WVA_OK;
+}
+
+int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
+    GridArgs& g = plan.args;
+    const HostFleet& hf = h->hf;
+    size_t slot_doubles;
+    int Kmax;
+    int rc = ensure_scratch(h, plan.Bmax, hf.tun.max_queue_to_batch_ratio, &slot_doubles, &Kmax);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_k0, h->stream));
+    if (g.n_items > 0) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_kernel, 256, 0));
+        per_sm = std::max(1, std::min(per_sm, 8));
+        const unsigned warps_needed = g.n_items;
+        unsigned blocks = (unsigned)(h->sm_count * per_sm);
+        blocks = std::min(blocks, (warps_needed + 7) / 8);
+        grid_kernel<<<blocks, 256, 0, h->stream>>>(g);
+        h->launches++;
+    }
+    CK(cudaEventRecord(h->ev_k1, h->stream));
+    if (g.n_items > 0) {
+        grid_fallback<<<kFbBlocks, kFbThreads, 0, h->stream>>>(g, (double*)h->d_scratch.p, slot_doubles, Kmax,
+                                                               (Cand*)h->d_fb_cands.p,
+                                                               (int*)h->d_ctrl.p + CTRL_FB_STATUS);
+        h->launches++;
+    }
+    if (hf.S > 0) {
+        grid_finalize<<<hf.S, 128, 0, h->stream>>>(g, (const Cand*)h->d_fb_cands.p, winners);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    return WVA_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+void wva_tunables_default(wva_tunables* t) {
+    if (!t) return;
+    t->max_queue_to_batch_ratio = 10;  // pkg/config/defaults.go:18
+    t->accel_penalty_factor = 0.1f;    // pkg/config/defaults.go:21
+}
+
+int wva_abi_version(void) { return WVA_ABI_VERSION; }
+
+const char* wva_strerror(int code) {
+    switch (code) {
+    case WVA_OK: return "ok";
+    case WVA_ERR_BAD_ARG: return "bad argument";
+    case WVA_ERR_NO_DEVICE: return "no CUDA device";
+    case WVA_ERR_CUDA: return "CUDA runtime error";
+    case WVA_ERR_NOMEM: return "out of memory";
+    case WVA_ERR_STATE: return "call sequence error";
+    case WVA_ERR_UNSUPPORTED: return "input outside the supported domain";
+    default: return "unknown error";
+    }
+}
+
+const char* wva_last_error(const wva_handle* h) { return h ? h->err.c_str() : ""; }
+
+int wva_create(wva_handle** out, int device) {
+    if (!out) return WVA_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return WVA_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return WVA_ERR_NO_DEVICE;
+    wva_handle* h = new (std::nothrow) wva_handle();
+    if (!h) return WVA_ERR_NOMEM;
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev_k0) != cudaSuccess || cudaEventCreate(&h->ev_k1) != cudaSuccess ||
+        cudaEventCreate(&h->ev_d0) != cudaSuccess || cudaEventCreate(&h->ev_d1) != cudaSuccess) {
+        delete h;
+        return WVA_ERR_CUDA;
+    }
+    *out = h;
+    return WVA_OK;
+}
+
+void wva_destroy(wva_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->arena, &h->d_cand_pair, &h->d_cand_N, &h->d_group_off, &h->d_ltab, &h->d_grid_lists,
+                      &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_partials,
+                      &h->d_cand_block, &h->d_win_block, &h->d_ctrl, &h->d_fb_list, &h->d_fb_cands, &h->d_scratch,
+                      &h->d_cells, &h->d_sweep};
+    for (DevBuf* b : bufs) b->release();
+    h->stage.release();
+    h->out_stage.release();
+    if (h->ev_k0) cudaEventDestroy(h->ev_k0);
+    if (h->ev_k1) cudaEventDestroy(h->ev_k1);
+    if (h->ev_d0) cudaEventDestroy(h->ev_d0);
+    if (h->ev_d1) cudaEventDestroy(h->ev_d1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+void* wva_stream(wva_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int wva_synchronize(wva_handle* h) {
+    if (!h) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return WVA_OK;
+}
+
+int64_t wva_launch_count(const wva_handle* h) { return h ? h->launches : 0; }
+float wva_last_kernel_ms(const wva_handle* h) { return h ? h->last_kernel_ms : 0.f; }
+float wva_last_device_ms(const wva_handle* h) { return h ? h->last_device_ms : 0.f; }
+
+int wva_upload(wva_handle* h, const wva_fleet* fleet) {
+    if (!h) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = upload_fleet(h, fleet);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return WVA_OK;
+}
+
+int wva_update_load(wva_handle* h, const float* arrival_rpm, const int32_t* in_tokens, const int32_t* out_tokens) {
+    if (!h) return WVA_ERR_BAD_ARG;
+    if (!h->resident) return h->fail(WVA_ERR_STATE, "no resident fleet (call wva_upload first)");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));  // the pinned stage may still feed an earlier async copy
+    HostFleet& hf = h->hf;
+    const size_t S = hf.S;
+    bool tokens_changed = false, class_changed = false;
+    if (arrival_rpm) {
+        for (size_t s = 0; s < S && !class_changed; ++s)
+            class_changed = ((arrival_rpm[s] == 0.0f) != (hf.srv_arrival_rpm[s] == 0.0f)) ||
+                            ((arrival_rpm[s] < 0.0f) != (hf.srv_arrival_rpm[s] < 0.0f));
+        hf.srv_arrival_rpm.assign(arrival_rpm, arrival_rpm + S);
+        memcpy((char*)h->stage.p + h->col_rate.off, arrival_rpm, 4 * S);
+    }
+    if (in_tokens) {
+        tokens_changed = tokens_changed || !std::equal(in_tokens, in_tokens + S, hf.srv_in_tokens.begin());
+        hf.srv_in_tokens.assign(in_tokens, in_tokens + S);
+        memcpy((char*)h->stage.p + h->col_in.off, in_tokens, 4 * S);
+    }
+    if (out_tokens) {
+        tokens_changed = tokens_changed || !std::equal(out_tokens, out_tokens + S, hf.srv_out_tokens.begin());
+        hf.srv_out_tokens.assign(out_tokens, out_tokens + S);
+        memcpy((char*)h->stage.p + h->col_out.off, out_tokens, 4 * S);
+    }
+    // the three load columns are adjacent in the arena: one copy
+    const size_t lo = h->col_rate.off, hi = h->col_out.off + h->col_out.bytes;
+    if (S) CK(cudaMemcpyAsync((char*)h->arena.p + lo, (char*)h->stage.p + lo, hi - lo, cudaMemcpyHostToDevice, h->stream));
+    if (tokens_changed || class_changed) h->epoch_tokens++;
+    return WVA_OK;
+}
+
+int wva_analyze(wva_handle* h, const wva_fleet* fleet, wva_allocs* candidates) {
+    if (!h || !candidates) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = upload_fleet(h, fleet);
+    if (rc) return rc;
+    // Server.Calculate also assigns value = transition penalty: run the unlimited
+    // kernel into a scratch winner block so that candidate values are final
+    wva_allocs dummy{};
+    return run_size_host(h, candidates, &dummy);
+}
+
+int wva_resolve(wva_handle* h, wva_allocs* candidates, wva_allocs* winners) {
+    if (!h || !winners) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!h->resident) return h->fail(WVA_ERR_STATE, "no resident fleet (call wva_upload first)");
+    if (!h->hf.unlimited) return h->fail(WVA_ERR_UNSUPPORTED, "limited (greedy) mode is not implemented yet");
+    return run_size_host(h, candidates, winners);
+}
+
+int wva_solve(wva_handle* h, const wva_fleet* fleet, wva_allocs* candidates, wva_allocs* winners) {
+    if (!h || !winners) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = upload_fleet(h, fleet);
+    if (rc) return rc;
+    return wva_resolve(h, candidates, winners);
+}
+
+int wva_resolve_device(wva_handle* h, wva_allocs* winners_dev) {
+    if (!h || !winners_dev) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!h->resident) return h->fail(WVA_ERR_STATE, "no resident fleet (call wva_upload first)");
+    if (!h->hf.unlimited) return h->fail(WVA_ERR_UNSUPPORTED, "limited (greedy) mode is not implemented yet");
+    const HostFleet& hf = h->hf;
+    const Block bc = block_layout((size_t)hf.S * hf.A);
+    CK(h->d_cand_block.ensure(bc.bytes + 16));
+    const AllocCols dc = block_cols(h->d_cand_block.p, bc);
+    const AllocCols dw = cols_from_abi(winners_dev);
+    CK(cudaEventRecord(h->ev_d0, h->stream));
+    int rc = enqueue_size(h, dc, &dw);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_d1, h->stream));
+    return WVA_OK;
+}
+
+int wva_grid_solve_device(wva_handle* h, const wva_grid* grid, wva_allocs* winners_dev) {
+    if (!h || !winners_dev) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!h->resident) return h->fail(WVA_ERR_STATE, "no resident fleet (call wva_upload first)");
+    int rc = validate_grid(h, grid);
+    if (rc) return rc;
+    rc = ensure_ctrl(h);
+    if (rc) return rc;
+    GridPlan plan;
+    rc = prepare_grid(h, grid, &plan);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_d0, h->stream));
+    rc = enqueue_grid(h, plan, cols_from_abi(winners_dev));
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_d1, h->stream));
+    return WVA_OK;
+}
+
+int wva_grid_solve(wva_handle* h, const wva_fleet* fleet, const wva_grid* grid, wva_cells* cells, wva_allocs* winners) {
+    if (!h || !winners) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = validate_grid(h, grid);
+    if (rc) return rc;
+    rc = upload_fleet(h, fleet);
+    if (rc) return rc;
+    rc = ensure_ctrl(h);
+    if (rc) return rc;
+    GridPlan plan;
+    rc = prepare_grid(h, grid, &plan);
+    if (rc) return rc;
+    const HostFleet& hf = h->hf;
+    const Block bw = block_layout(hf.S);
+    CK(h->d_win_block.ensure(bw.bytes + 16));
+    const AllocCols dw = block_cols(h->d_win_block.p, bw);
+    // optional per-cell table: flags u8 + 4 float columns
+    const size_t nc = plan.n_cells;
+    const bool want_cells = cells && (cells->flags || cells->ttft || cells->itl || cells->rho || cells->throughput);
+    size_t cell_bytes = 0;
+    if (want_cells) {
+        cell_bytes = align_up(nc) + 4 * align_up(4 * nc);
+        CK(h->d_cells.ensure(cell_bytes));
+        char* p = (char*)h->d_cells.p;
+        plan.args.cells.flags = (uint8_t*)p;
+        plan.args.cells.ttft = (float*)(p + align_up(nc));
+        plan.args.cells.itl = (float*)(p + align_up(nc) + align_up(4 * nc));
+        plan.args.cells.rho = (float*)(p + align_up(nc) + 2 * align_up(4 * nc));
+        plan.args.cells.throughput = (float*)(p + align_up(nc) + 3 * align_up(4 * nc));
+        CK(cudaMemsetAsync(p, 0, cell_bytes, h->stream));
+    }
+    CK(cudaEventRecord(h->ev_d0, h->stream));
+    rc = enqueue_grid(h, plan, dw);
+    if (rc) return rc;
+    const size_t stage_bytes = align_up(bw.bytes) + 256;
+    CK(h->out_stage.ensure(stage_bytes));
+    char* hs = (char*)h->out_stage.p;
+    if (bw.bytes) CK(cudaMemcpyAsync(hs, h->d_win_block.p, bw.bytes, cudaMemcpyDeviceToHost, h->stream));
+    int* ctrl_host = (int*)(hs + align_up(bw.bytes));
+    CK(cudaMemcpyAsync(ctrl_host, h->d_ctrl.p, CTRL_INTS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (want_cells && nc) {
+        const char* p = (const char*)h->d_cells.p;
+        if (cells->flags) CK(cudaMemcpyAsync(cells->flags, p, nc, cudaMemcpyDeviceToHost, h->stream));
+        if (cells->ttft) CK(cudaMemcpyAsync(cells->ttft, p + align_up(nc), 4 * nc, cudaMemcpyDeviceToHost, h->stream));
+        if (cells->itl)
+            CK(cudaMemcpyAsync(cells->itl, p + align_up(nc) + align_up(4 * nc), 4 * nc, cudaMemcpyDeviceToHost, h->stream));
+        if (cells->rho)
+            CK(cudaMemcpyAsync(cells->rho, p + align_up(nc) + 2 * align_up(4 * nc), 4 * nc, cudaMemcpyDeviceToHost, h->stream));
+        if (cells->throughput)
+            CK(cudaMemcpyAsync(cells->throughput, p + align_up(nc) + 3 * align_up(4 * nc), 4 * nc, cudaMemcpyDeviceToHost,
+                               h->stream));
+    }
+    rc = finish_timing(h);
+    if (rc) return rc;
+    rc = check_fallback_status(h, ctrl_host, plan.args.fb_cap);
+    if (rc) return rc;
+    scatter_block(hs, bw, winners);
+    return WVA_OK;
+}
+
+int wva_sweep(wva_handle* h, const wva_fleet* fleet, int32_t n_rates, wva_sweep_out* out) {
+    if (!h || !out || n_rates < 1) return WVA_ERR_BAD_ARG;
+    if (!out->valid || !out->rate || !out->ttft || !out->itl || !out->throughput || !out->rho)
+        return h->fail(WVA_ERR_BAD_ARG, "NULL sweep output column");
+    CK(cudaSetDevice(h->device));
+    int rc = upload_fleet(h, fleet);
+    if (rc) return rc;
+    rc = ensure_ctrl(h);
+    if (rc) return rc;
+    const HostFleet& hf = h->hf;
+    const int A = hf.A, S = hf.S;
+    // every (server, acc) with a profile, ignoring keepAccelerator; sorted by descending N
+    std::vector<int> pairs, Ns((size_t)S * A, 0);
+    for (int s = 0; s < S; ++s)
+        for (int a = 0; a < A; ++a) {
+            const int m = hf.srv_model[s];
+            if (hf.srv_in_tokens[s] < 0 || hf.srv_out_tokens[s] < 1 || m < 0 || m >= hf.M ||
+                !hf.perf_present[(size_t)m * A + a])
+                continue;
+            const int N = hf.pair_batch(s, a);
+            if (N > (1 << 20)) return h->fail(WVA_ERR_UNSUPPORTED, "batch size above 2^20");
+            Ns[(size_t)s * A + a] = N;
+            pairs.push_back(s * A + a);
+        }
+    std::stable_sort(pairs.begin(), pairs.end(), [&](int x, int y) { return Ns[x] > Ns[y]; });
+    const int n = (int)pairs.size();
+    std::vector<int> lens(n);
+    std::vector<long long> offs(n);
+    long long off = 0;
+    for (int e = 0; e < n; ++e) {
+        lens[e] = Ns[pairs[e]];
+        offs[e] = off;
+        off += lens[e];
+    }
+    const size_t n_out = (size_t)S * A * n_rates;
+    const size_t out_bytes = align_up(n_out) + 5 * align_up(4 * n_out);
+    CK(h->d_sweep.ensure(std::max<size_t>(out_bytes, 256)));
+    char* p = (char*)h->d_sweep.p;
+    CK(cudaMemsetAsync(p, 0, std::max<size_t>(out_bytes, 256), h->stream));
+    CK(cudaEventRecord(h->ev_d0, h->stream));
+    CK(cudaEventRecord(h->ev_k0, h->stream));
+    if (n) {
+        CK(h->d_tab_pair.ensure(sizeof(int) * n));
+        CK(h->d_tab_off.ensure(sizeof(long long) * n));
+        CK(h->d_tab_len.ensure(sizeof(int) * n));
+        CK(h->d_tab.ensure(sizeof(double) * 3 * (size_t)off));
+        CK(cudaMemcpyAsync(h->d_tab_pair.p, pairs.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_tab_off.p, offs.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_tab_len.p, lens.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        h->grid_epoch = ~0ull;  // the shared-table buffers now hold sweep tables
+        build_pair_tables<<<n, 128, 0, h->stream>>>(h->df, (const int*)h->d_tab_pair.p, (const long long*)h->d_tab_off.p,
+                                                    (const int*)h->d_tab_len.p, n, (double*)h->d_tab.p);
+        h->launches++;
+        SweepArgs g{};
+        g.f = h->df;
+        g.pair_list = (const int*)h->d_tab_pair.p;
+        g.pair_N = (const int*)h->d_tab_len.p;
+        g.tab_off = (const long long*)h->d_tab_off.p;
+        g.tab = (const double*)h->d_tab.p;
+        g.n_pairs = n;
+        g.n_rates = n_rates;
+        g.n_chunks = (n_rates + 31) / 32;
+        g.counter = (unsigned*)h->d_ctrl.p + CTRL_COUNTER;
+        g.valid = (uint8_t*)p;
+        g.rate = (float*)(p + align_up(n_out));
+        g.ttft = (float*)(p + align_up(n_out) + align_up(4 * n_out));
+        g.itl = (float*)(p + align_up(n_out) + 2 * align_up(4 * n_out));
+        g.throughput = (float*)(p + align_up(n_out) + 3 * align_up(4 * n_out));
+        g.rho = (float*)(p + align_up(n_out) + 4 * align_up(4 * n_out));
+        g.fb_count = (int*)h->d_ctrl.p + CTRL_FB_COUNT;
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel, 256, 0));
+        per_sm = std::max(1, std::min(per_sm, 8));
+        const unsigned items = (unsigned)n * g.n_chunks;
+        unsigned blocks = std::min<unsigned>((unsigned)(h->sm_count * per_sm), (items + 7) / 8);
+        CK(cudaEventRecord(h->ev_k0, h->stream));
+        sweep_kernel<<<blocks, 256, 0, h->stream>>>(g);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(h->ev_k1, h->stream));
+    CK(h->out_stage.ensure(256));
+    int* ctrl_host = (int*)h->out_stage.p;
+    CK(cudaMemcpyAsync(ctrl_host, h->d_ctrl.p, CTRL_INTS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (n_out) {
+        CK(cudaMemcpyAsync(out->valid, p, n_out, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out->rate, p + align_up(n_out), 4 * n_out, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out->ttft, p + align_up(n_out) + align_up(4 * n_out), 4 * n_out, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out->itl, p + align_up(n_out) + 2 * align_up(4 * n_out), 4 * n_out, cudaMemcpyDeviceToHost,
+                           h->stream));
+        CK(cudaMemcpyAsync(out->throughput, p + align_up(n_out) + 3 * align_up(4 * n_out), 4 * n_out,
+                           cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out->rho, p + align_up(n_out) + 4 * align_up(4 * n_out), 4 * n_out, cudaMemcpyDeviceToHost,
+                           h->stream));
+    }
+    rc = finish_timing(h);
+    if (rc) return rc;
+    if (ctrl_host[CTRL_FB_COUNT] != 0)
+        return h->fail(WVA_ERR_UNSUPPORTED, "sweep point outside the streaming solve's numeric window");
+    return WVA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+// wva_device.cuh — device-side restatement of pkg/analyzer for sm_100a.
+//
+// Arithmetic contract: bit-identical to the Go reference on amd64 (binary32/64, RNE, no
+// FMA contraction).  Every float/double operation of the reference is issued here as an
+// explicitly rounded intrinsic (__fmul_rn, __dadd_rn, ...) so the compiler can neither
+// contract nor reorder it; the translation unit is also compiled with -fmad=false.
+//
+// The one place where the instruction sequence differs from the reference is IEEE
+// division by a value that is reused many times (the state-dependent service rate and
+// the normalising sum).  There the quotient is produced by a Markstein correction
+// around a pre-computed double-word reciprocal, which yields the correctly rounded
+// quotient — the same bits as the reference's DIVSD — in 4 dependent FP64 ops instead
+// of the ~10-op generic division sequence (see DESIGN.md "Exact division").
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace wva {
+
+// ---------------------------------------------------------------------------
+// Go builtin min/max on float32 (NaN-propagating, -0 < +0).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float go_minf(float a, float b) {
+    if (isnan(a) || isnan(b)) return __int_as_float(0x7fc00000);
+    if (a == 0.0f && b == 0.0f) return signbit(a) ? a : b;
+    return a < b ? a : b;
+}
+__device__ __forceinline__ float go_maxf(float a, float b) {
+    if (isnan(a) || isnan(b)) return __int_as_float(0x7fc00000);
+    if (a == 0.0f && b == 0.0f) return signbit(a) ? b : a;
+    return a > b ? a : b;
+}
+// Go int(float64) on amd64 (CVTTSD2SQ): "integer indefinite" on NaN / overflow.
+__device__ __forceinline__ long long go_f64_to_int(double x) {
+    if (!(x >= -9223372036854775808.0 && x < 9223372036854775808.0)) return LLONG_MIN;
+    return (long long)x;
+}
+
+// ---------------------------------------------------------------------------
+// Service-time model: pkg/analyzer/queueanalyzer.go:257-266, 296-302, 99-118.
+// ---------------------------------------------------------------------------
+struct QParams {
+    float alpha, beta, gamma, delta;
+    int in_tok, out_tok;
+};
+
+__device__ __forceinline__ float prefill_time(const QParams& q, float batch) {  // :257-262
+    if (q.in_tok == 0) return 0.0f;
+    float t = __fmul_rn(q.delta, (float)q.in_tok);
+    t = __fmul_rn(t, batch);
+    return __fadd_rn(q.gamma, t);
+}
+__device__ __forceinline__ float decode_time(const QParams& q, float batch) {  // :264-266
+    return __fadd_rn(q.alpha, __fmul_rn(q.beta, batch));
+}
+__device__ __forceinline__ float effective_concurrency(const QParams& q, float avg_serv_time, int max_batch) {
+    float tokens = (float)(q.out_tok - 1);  // :296-302
+    float base = __fadd_rn(q.gamma, __fmul_rn(q.alpha, tokens));
+    float numerator = __fsub_rn(avg_serv_time, base);
+    float denominator = __fadd_rn(__fmul_rn(q.delta, (float)q.in_tok), __fmul_rn(q.beta, tokens));
+    float n = __fdiv_rn(numerator, denominator);
+    return go_minf(go_maxf(n, 0.0f), (float)max_batch);
+}
+// servRate[n-1], n >= 1: BuildModel, queueanalyzer.go:104-113
+__device__ __forceinline__ float serv_rate(const QParams& q, int n) {
+    float fn = (float)n;
+    float prefill = prefill_time(q, fn);
+    int num_decode = q.out_tok - 1;
+    if (q.in_tok == 0 && q.out_tok == 1) num_decode = 1;
+    float decode = __fmul_rn((float)num_decode, decode_time(q, fn));
+    return __fdiv_rn(fn, __fadd_rn(prefill, decode));
+}
+// RateRange (req/sec) from servRate[0] and servRate[N-1]: queueanalyzer.go:116-118
+__device__ __forceinline__ float rate_min_of(float s1) { return __fmul_rn(__fmul_rn(s1, 0.001f), 1000.0f); }
+__device__ __forceinline__ float rate_max_of(float sN) {
+    return __fmul_rn(__fmul_rn(sN, __fsub_rn(1.0f, 0.001f)), 1000.0f);
+}
+
+// ---------------------------------------------------------------------------
+// Exact division by a reused divisor.
+// ---------------------------------------------------------------------------
+struct Recip {  // b with its double-word reciprocal yh + yl ~= 1/b (yh = RN(1/b))
+    double b, yh, yl;
+};
+__device__ __forceinline__ Recip make_recip(double b) {
+    Recip r;
+    r.b = b;
+    r.yh = __ddiv_rn(1.0, b);
+    double e = __fma_rn(-b, r.yh, 1.0);  // exact: yh is the correctly rounded reciprocal
+    r.yl = __ddiv_rn(e, b);
+    return r;
+}
+// RN(a / b).  q0 = RN(a*(yh+yl)) is a faithful quotient (pre-rounding relative error
+// ~2^-104); Markstein's theorem then gives RN(q0 + RN(a - b*q0)*yh) = RN(a/b) exactly,
+// provided no intermediate leaves the normal range — callers guarantee that with the
+// exponent-window tests below.
+__device__ __forceinline__ double div_recip(double a, const Recip& r) {
+    double t = __dmul_rn(a, r.yl);
+    double q0 = __fma_rn(a, r.yh, t);
+    double res = __fma_rn(-r.b, q0, a);
+    return __fma_rn(res, r.yh, q0);
+}
+
+// Exponent windows (high 32 bits of the double).  p in [2^-280, 2^600) keeps every
+// intermediate of both reciprocal divisions normal when lambda and the service rates
+// lie in [2^-60, 2^60] and the normalising sum is < 2^620 (derivation in DESIGN.md).
+#define WVA_HI(e) ((unsigned)((1023 + (e)) << 20))
+__device__ __forceinline__ bool in_window(double p, unsigned lo, unsigned hi) {
+    return ((unsigned)__double2hiint(p) - lo) < (hi - lo);
+}
+constexpr unsigned kHiPLo = WVA_HI(-280);
+constexpr unsigned kHiPHi = WVA_HI(600);
+constexpr unsigned kHiRateLo = WVA_HI(-60);
+constexpr unsigned kHiRateHi = WVA_HI(60);
+constexpr unsigned kHiSumLo = WVA_HI(0);
+constexpr unsigned kHiSumHi = WVA_HI(620);
+
+// ---------------------------------------------------------------------------
+// MM1ModelStateDependent: pkg/analyzer/mm1modelstatedependent.go:38-116.
+//
+// The reference stores p[0..K] and makes four passes over it.  Here nothing is stored:
+// pass 1 runs the recurrence p[n+1] = (p[n]*lambda)/servRate[min(n,N-1)] keeping only
+// the running sum (same summation order as :93-105); pass 2 re-runs the identical
+// recurrence (identical roundings, so identical p[n]), normalises each p[n] by the sum
+// (:108-112) and accumulates sum(i*p[i]) and sumP in the reference's order (:47-55).
+// The overflow-rescale branches (:84-89, :96-104) cannot be reproduced without the
+// stored vector; when a value leaves the safe window the solve reports kSolveBail and
+// the caller re-runs the cell on the stored-vector fallback (solve_stored below).
+// ---------------------------------------------------------------------------
+enum { kSolveOk = 0, kSolveBail = 1 };
+
+struct ModelStats {  // queuemodel.go:10-19 + mm1kmodel.go:15 + mm1modelstatedependent.go:12
+    float throughput, avg_resp_time, avg_wait_time, avg_serv_time, avg_num_in_servers;
+};
+
+// Head tables.  TAB_SHARED: one table per (server, accelerator) pair, read at the same
+// address by every lane of a warp: 3 doubles per n (servRate, yh, yl).  TAB_LANE: one
+// float32 servRate column per lane, element n at tab[n * stride] (coalesced across the
+// warp); the head then uses the generic IEEE division.
+enum { TAB_SHARED = 0, TAB_LANE = 1 };
+
+template <int TAB>
+__device__ __forceinline__ double head_rate(const void* tab, int stride, int n) {
+    if (TAB == TAB_SHARED) return ((const double*)tab)[3 * n];
+    return (double)((const float*)tab)[(size_t)n * stride];
+}
+template <int TAB>
+__device__ __forceinline__ double head_step_fast(const void* tab, int stride, int n, double a) {
+    if (TAB == TAB_SHARED) {
+        const double* t = (const double*)tab + 3 * n;
+        Recip r;
+        r.b = t[0];
+        r.yh = t[1];
+        r.yl = t[2];
+        return div_recip(a, r);
+    }
+    return __ddiv_rn(a, (double)((const float*)tab)[(size_t)n * stride]);
+}
+
+// Returns kSolveOk / kSolveBail.  N = len(servRate), K = occupancy upper bound (>= 2),
+// lam = float64(lambda), tail = servRate[N-1] with its reciprocal.
+template <int TAB>
+__device__ __noinline__ int solve_model(const void* tab, int stride, int N, int K, float lambda, const Recip& tail,
+                                        ModelStats& st) {
+    const double lam = (double)lambda;
+    if (!in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail.b, kHiRateLo, kHiRateHi)) return kSolveBail;
+    const int nh = N - 1;  // steps n < nh read servRate[n] from the table; the rest use the tail
+
+    // ---- pass 1: normalising sum ------------------------------------------------
+    double p = 1.0, sum = 1.0;
+    {
+        int n = 0;
+        bool zero = false;
+        for (; n < nh; ++n) {
+            if (in_window(p, kHiPLo, kHiPHi)) {
+                p = head_step_fast<TAB>(tab, stride, n, __dmul_rn(p, lam));
+            } else {
+                if (p == 0.0) { zero = true; break; }
+                if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
+                p = __ddiv_rn(__dmul_rn(p, lam), head_rate<TAB>(tab, stride, n));
+            }
+            sum = __dadd_rn(sum, p);
+        }
+        if (!zero) {
+#pragma unroll 4
+            for (; n < K; ++n) {
+                if (in_window(p, kHiPLo, kHiPHi)) {
+                    p = div_recip(__dmul_rn(p, lam), tail);
+                } else {
+                    if (p == 0.0) break;
+                    if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
+                    p = __ddiv_rn(__dmul_rn(p, lam), tail.b);
+                }
+                sum = __dadd_rn(sum, p);
+            }
+        }
+    }
+    if (!in_window(sum, kHiSumLo, kHiSumHi)) return kSolveBail;
+
+    // ---- pass 2: normalise, accumulate -----------------------------------------
+    const Recip z = make_recip(sum);
+    const double pn0 = z.yh;  // p[0]/sum = RN(1/sum)
+    double acc = 0.0, sum_p = pn0, in_serv = 0.0, pn = pn0, di = 1.0;
+    const double dN = (double)N;
+    // p[1] from p[0] = 1: RN(1*lambda) = lambda
+    p = (nh > 0) ? head_step_fast<TAB>(tab, stride, 0, lam) : div_recip(lam, tail);
+    int i = 1;
+    bool done = false;
+    // states 1..N: also feed sumP and capture avgNumInServers at i == N (:50-54)
+    for (; i <= N; ++i) {
+        const bool fast = in_window(p, kHiPLo, kHiPHi);
+        if (fast) {
+            pn = div_recip(p, z);
+        } else {
+            if (p == 0.0) { pn = 0.0; done = true; break; }
+            if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
+            pn = __ddiv_rn(p, sum);
+        }
+        acc = __dadd_rn(acc, __dmul_rn(di, pn));
+        sum_p = __dadd_rn(sum_p, pn);
+        di = __dadd_rn(di, 1.0);
+        if (i < K) {
+            const double a = __dmul_rn(p, lam);
+            if (fast) {
+                p = (i < nh) ? head_step_fast<TAB>(tab, stride, i, a) : div_recip(a, tail);
+            } else {
+                p = __ddiv_rn(a, (i < nh) ? head_rate<TAB>(tab, stride, i) : tail.b);
+            }
+        }
+    }
+    // i == N was reached (or every later p is exactly 0, which leaves acc and sumP unchanged)
+    in_serv = __dadd_rn(acc, __dmul_rn(__dsub_rn(1.0, sum_p), dN));
+    if (!done) {
+#pragma unroll 2
+        for (; i <= K; ++i) {
+            const bool fast = in_window(p, kHiPLo, kHiPHi);
+            if (fast) {
+                pn = div_recip(p, z);
+            } else {
+                if (p == 0.0) { pn = 0.0; break; }
+                if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
+                pn = __ddiv_rn(p, sum);
+            }
+            acc = __dadd_rn(acc, __dmul_rn(di, pn));
+            di = __dadd_rn(di, 1.0);
+            if (i < K) {
+                const double a = __dmul_rn(p, lam);
+                p = fast ? div_recip(a, tail) : __ddiv_rn(a, tail.b);
+            }
+        }
+    }
+    // pn now holds p[K] (0 if the chain died out)
+
+    // ---- float32 tail: mm1modelstatedependent.go:56-66 --------------------------
+    st.avg_num_in_servers = (float)in_serv;
+    const float avg_num_in_system = (float)acc;
+    st.throughput = __fmul_rn(lambda, __fsub_rn(1.0f, (float)pn));
+    st.avg_resp_time = __fdiv_rn(avg_num_in_system, st.throughput);
+    st.avg_serv_time = __fdiv_rn(st.avg_num_in_servers, st.throughput);
+    float w = __fsub_rn(st.avg_resp_time, st.avg_serv_time);
+    if (w < 0.0f) w = 0.0f;
+    st.avg_wait_time = w;
+    return kSolveOk;
+}
+
+// Stored-vector fallback: a literal restatement of computeProbabilities /
+// computeStatistics on a scratch p[0..K] in global memory, including the overflow
+// rescale loops.  Used only for cells the streaming solve bailed out of.
+// Returns 0 ok, 2 = the reference's rescale loop would not terminate (unsupported input).
+__device__ __noinline__ int solve_stored(double* p, const float* serv_rate, int N, int K, float lambda, ModelStats& st) {
+    const double lam = (double)lambda;
+    p[0] = 1.0;
+    const double scale = __ddiv_rn(1.7976931348623157e308, (double)K);
+    for (int n = 0; n < K; ++n) {
+        const double s_rate = (double)serv_rate[n < N ? n : N - 1];
+        double v = __ddiv_rn(__dmul_rn(p[n], lam), s_rate);
+        int guard = 0;
+        while (v < 0.0 || isinf(v) || isnan(v)) {
+            if (++guard > 64) return 2;
+            for (int i = 0; i <= n; ++i) p[i] = __ddiv_rn(p[i], scale);
+            v = __ddiv_rn(__dmul_rn(p[n], lam), s_rate);
+        }
+        p[n + 1] = v;
+    }
+    double sum = 0.0;
+    for (int n = 0; n <= K; ++n) {
+        sum = __dadd_rn(sum, p[n]);
+        if (sum < 0.0 || isinf(sum)) {
+            sum = 0.0;
+            for (int i = 0; i <= K; ++i) {
+                p[i] = __ddiv_rn(p[i], scale);
+                if (i <= n) sum = __dadd_rn(sum, p[i]);
+            }
+        }
+    }
+    for (int n = 0; n <= K; ++n) p[n] = __ddiv_rn(p[n], sum);
+    double acc = 0.0, in_serv = 0.0, sum_p = p[0];
+    for (int i = 1; i <= K; ++i) {
+        acc = __dadd_rn(acc, __dmul_rn((double)i, p[i]));
+        sum_p = __dadd_rn(sum_p, p[i]);
+        if (i == N) in_serv = __dadd_rn(acc, __dmul_rn(__dsub_rn(1.0, sum_p), (double)N));
+    }
+    st.avg_num_in_servers = (float)in_serv;
+    const float avg_num_in_system = (float)acc;
+    st.throughput = __fmul_rn(lambda, __fsub_rn(1.0f, (float)p[K]));
+    st.avg_resp_time = __fdiv_rn(avg_num_in_system, st.throughput);
+    st.avg_serv_time = __fdiv_rn(st.avg_num_in_servers, st.throughput);
+    float w = __fsub_rn(st.avg_resp_time, st.avg_serv_time);
+    if (w < 0.0f) w = 0.0f;
+    st.avg_wait_time = w;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// QueueAnalyzer.Analyze metrics from solved model stats: queueanalyzer.go:152-172.
+// ---------------------------------------------------------------------------
+struct Metrics {
+    float throughput, avg_wait_time, avg_prefill_time, avg_token_time, rho, ttft;
+};
+__device__ __forceinline__ Metrics metrics_from(const QParams& q, int N, const ModelStats& st) {
+    Metrics m;
+    const float eff = effective_concurrency(q, st.avg_serv_time, N);
+    m.avg_prefill_time = prefill_time(q, eff);
+    m.avg_token_time = decode_time(q, eff);
+    float rho = __fdiv_rn(st.avg_num_in_servers, (float)N);
+    m.rho = go_minf(go_maxf(rho, 0.0f), 1.0f);
+    m.throughput = __fmul_rn(st.throughput, 1000.0f);
+    m.avg_wait_time = st.avg_wait_time;
+    m.ttft = __fadd_rn(st.avg_wait_time, m.avg_prefill_time);
+    return m;
+}
+
+// WithinTolerance: pkg/analyzer/utils.go:12-20
+__device__ __forceinline__ bool within_tolerance(float x, float value, float tol) {
+    if (x == value) return true;
+    if (value == 0.0f || tol < 0.0f) return false;
+    return fabs((double)__fdiv_rn(__fsub_rn(x, value), value)) <= (double)tol;
+}
+
+// TransitionPenalty: pkg/core/allocation.go:291-300
+__device__ __forceinline__ float transition_penalty(float factor, int cur_acc, int cur_replicas, float cur_cost,
+                                                    int new_acc, int new_replicas, float new_cost) {
+    if (cur_acc == new_acc && cur_acc != -2) {
+        if (cur_replicas == new_replicas) return 0.0f;
+        return __fsub_rn(new_cost, cur_cost);
+    }
+    return __fadd_rn(__fmul_rn(factor, __fadd_rn(cur_cost, new_cost)), __fsub_rn(new_cost, cur_cost));
+}
+
+}  // namespace wva

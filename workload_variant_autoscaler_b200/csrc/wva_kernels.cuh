@@ -1,0 +1,706 @@
+// wva_kernels.cuh — sm_100a kernels of the WVA optimizer hot path.
+//
+//   build_pair_tables   servRate[n] (+ double-word reciprocal) per (server, accelerator)
+//   grid_kernel    K2   one Analyze per (server, acc, batch, replica) cell, persistent
+//                       warps pulling (server, batch, 32-cell chunk) items, fused
+//                       feasibility + cost + transition penalty + warp-shuffle argmin
+//   grid_fallback       stored-vector re-run of the rare cells the streaming solve bails on
+//   grid_finalize  K3   per-server argmin over partials (warp shuffle -> smem -> record)
+//   build_lane_tables   float32 servRate columns, coalesced per 32-candidate group
+//   size_kernel    K1   one CreateAllocation per (server, acc) candidate (2 bisections)
+//   size_fallback       stored-vector re-run of candidates that bailed
+//   trivial_kernel      nil / zero-load candidates
+//   unlimited_kernel    Server.Calculate value + SolveUnlimited argmin per server
+//   sweep_kernel        Analyze over a rate sweep per (server, acc)
+#pragma once
+#include "wva_device.cuh"
+
+namespace wva {
+
+// Device image of wva_fleet (all pointers are device pointers).
+struct DevFleet {
+    int A, T, M, S;
+    const float* acc_cost;
+    const int* acc_mult;
+    const int* acc_type;
+    const int* type_capacity;
+    const uint8_t* perf_present;
+    const float *perf_alpha, *perf_beta, *perf_gamma, *perf_delta;
+    const int *perf_acc_count, *perf_max_batch, *perf_at_tokens;
+    const int *srv_model, *srv_priority;
+    const uint8_t* srv_has_target;
+    const float *srv_slo_itl, *srv_slo_ttft, *srv_slo_tps;
+    const uint8_t* srv_keep_acc;
+    const int *srv_min_replicas, *srv_max_batch;
+    const float* srv_arrival_rpm;
+    const int *srv_in_tokens, *srv_out_tokens;
+    const int *srv_cur_acc, *srv_cur_replicas;
+    const float* srv_cur_cost;
+    int ratio;      // config.MaxQueueToBatchRatio
+    float penalty;  // config.AccelPenaltyFactor
+};
+
+// One candidate allocation (core.Allocation, pkg/core/allocation.go:13-24).
+struct Cand {
+    float value, cost;
+    int replicas, batch, acc;
+    float itl, ttft, rho, max_rate;
+    int feasible;
+};
+__device__ __forceinline__ Cand cand_nil() {
+    Cand c;
+    c.value = 0.f; c.cost = 0.f; c.replicas = 0; c.batch = 0; c.acc = -1;
+    c.itl = 0.f; c.ttft = 0.f; c.rho = 0.f; c.max_rate = 0.f; c.feasible = 0;
+    return c;
+}
+// Grid winner order: value, cost, replicas, batch, accelerator id (ascending).
+__device__ __forceinline__ bool cand_better(const Cand& x, const Cand& y) {
+    if (!x.feasible) return false;
+    if (!y.feasible) return true;
+    if (x.value != y.value) return x.value < y.value;
+    if (x.cost != y.cost) return x.cost < y.cost;
+    if (x.replicas != y.replicas) return x.replicas < y.replicas;
+    if (x.batch != y.batch) return x.batch < y.batch;
+    return x.acc < y.acc;
+}
+__device__ __forceinline__ Cand cand_shfl_down(const Cand& c, int d) {
+    Cand o;
+    o.value = __shfl_down_sync(0xffffffffu, c.value, d);
+    o.cost = __shfl_down_sync(0xffffffffu, c.cost, d);
+    o.replicas = __shfl_down_sync(0xffffffffu, c.replicas, d);
+    o.batch = __shfl_down_sync(0xffffffffu, c.batch, d);
+    o.acc = __shfl_down_sync(0xffffffffu, c.acc, d);
+    o.itl = __shfl_down_sync(0xffffffffu, c.itl, d);
+    o.ttft = __shfl_down_sync(0xffffffffu, c.ttft, d);
+    o.rho = __shfl_down_sync(0xffffffffu, c.rho, d);
+    o.max_rate = __shfl_down_sync(0xffffffffu, c.max_rate, d);
+    o.feasible = __shfl_down_sync(0xffffffffu, c.feasible, d);
+    return o;
+}
+__device__ __forceinline__ Cand cand_warp_min(Cand c) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        Cand o = cand_shfl_down(c, d);
+        if (cand_better(o, c)) c = o;
+    }
+    return c;
+}
+
+// SoA columns of wva_allocs on the device.
+struct AllocCols {
+    uint8_t* feasible;
+    int *acc, *replicas, *batch;
+    float *cost, *value, *itl, *ttft, *rho, *max_rate;
+};
+__device__ __forceinline__ void store_cand(const AllocCols& o, size_t i, const Cand& c) {
+    if (o.feasible) o.feasible[i] = (uint8_t)c.feasible;
+    if (o.acc) o.acc[i] = c.acc;
+    if (o.replicas) o.replicas[i] = c.replicas;
+    if (o.batch) o.batch[i] = c.batch;
+    if (o.cost) o.cost[i] = c.cost;
+    if (o.value) o.value[i] = c.value;
+    if (o.itl) o.itl[i] = c.itl;
+    if (o.ttft) o.ttft[i] = c.ttft;
+    if (o.rho) o.rho[i] = c.rho;
+    if (o.max_rate) o.max_rate[i] = c.max_rate;
+}
+__device__ __forceinline__ Cand load_cand(const AllocCols& o, size_t i) {
+    Cand c;
+    c.feasible = o.feasible[i]; c.acc = o.acc[i]; c.replicas = o.replicas[i]; c.batch = o.batch[i];
+    c.cost = o.cost[i]; c.value = o.value[i]; c.itl = o.itl[i]; c.ttft = o.ttft[i]; c.rho = o.rho[i];
+    c.max_rate = o.max_rate[i];
+    return c;
+}
+
+// ---------------------------------------------------------------------------
+// Gates of CreateAllocation (allocation.go:42-75) + candidate rule (server.go:70-82).
+// bit0: the pair can be analysed under load; bit1: zero-load candidate; 0: nil.
+// ---------------------------------------------------------------------------
+enum { PAIR_LOAD = 1, PAIR_ZERO = 2 };
+
+__device__ __forceinline__ int pair_class(const DevFleet& f, int s, int a, bool honour_keep) {
+    if (honour_keep && f.srv_keep_acc[s] && f.srv_cur_acc[s] != -1 && f.srv_cur_acc[s] != a) return 0;
+    if (f.srv_arrival_rpm[s] < 0.0f || f.srv_in_tokens[s] < 0 || f.srv_out_tokens[s] < 0) return 0;
+    const int m = f.srv_model[s];
+    if (m < 0 || m >= f.M) return 0;
+    if (!f.perf_present[m * f.A + a]) return 0;
+    if (!f.srv_has_target[s]) return 0;
+    if (f.srv_arrival_rpm[s] == 0.0f || f.srv_out_tokens[s] == 0) return PAIR_ZERO;
+    return PAIR_LOAD;
+}
+__device__ __forceinline__ int num_instances(const DevFleet& f, int m, int a) {  // model.go:50-57
+    const int c = f.perf_acc_count[m * f.A + a];
+    return c <= 0 ? 1 : c;
+}
+__device__ __forceinline__ QParams qparams_of(const DevFleet& f, int s, int a) {
+    const int k = f.srv_model[s] * f.A + a;
+    QParams q;
+    q.alpha = f.perf_alpha[k]; q.beta = f.perf_beta[k]; q.gamma = f.perf_gamma[k]; q.delta = f.perf_delta[k];
+    q.in_tok = f.srv_in_tokens[s]; q.out_tok = f.srv_out_tokens[s];
+    return q;
+}
+__device__ __forceinline__ float total_rate_of(const DevFleet& f, int s) {  // allocation.go:134-139
+    if (f.srv_slo_tps[s] == 0.0f) return __fdiv_rn(f.srv_arrival_rpm[s], 60.0f);
+    return __fdiv_rn(f.srv_slo_tps[s], (float)f.srv_out_tokens[s]);
+}
+__device__ __forceinline__ float penalty_of(const DevFleet& f, int s, const Cand& c) {
+    return transition_penalty(f.penalty, f.srv_cur_acc[s], f.srv_cur_replicas[s], f.srv_cur_cost[s], c.acc,
+                              c.replicas, c.cost);
+}
+// zeroLoadAllocation: allocation.go:259-288 (value = cost; caller applies the penalty)
+__device__ __forceinline__ Cand zero_load_alloc(const DevFleet& f, int s, int a) {
+    Cand c = cand_nil();
+    c.feasible = 1;
+    const long long nrep = f.srv_min_replicas[s];
+    if (nrep == 0) return c;  // accelerator "", all zero
+    const int m = f.srv_model[s], k = m * f.A + a;
+    int max_batch = f.perf_max_batch[k];
+    if (f.srv_max_batch[s] > 0) max_batch = f.srv_max_batch[s];
+    const long long total = (long long)num_instances(f, m, a) * nrep;
+    c.acc = a;
+    c.replicas = (int)nrep;
+    c.batch = max_batch;
+    c.cost = __fmul_rn(f.acc_cost[a], (float)total);
+    c.value = c.cost;
+    c.itl = __fadd_rn(f.perf_alpha[k], f.perf_beta[k]);
+    const float max_decode = __fadd_rn(f.perf_alpha[k], __fmul_rn(f.perf_beta[k], (float)max_batch));
+    c.ttft = __fadd_rn(f.perf_gamma[k], f.perf_delta[k]);
+    c.max_rate = __fdiv_rn((float)max_batch, __fadd_rn(c.ttft, max_decode));
+    return c;
+}
+
+// ---------------------------------------------------------------------------
+// Shared head tables: entry n (0-based) of pair t = {servRate[n], yh, yl} as doubles.
+// ---------------------------------------------------------------------------
+__global__ void build_pair_tables(DevFleet f, const int* __restrict__ tab_pair, const long long* __restrict__ tab_off,
+                                  const int* __restrict__ tab_len, int n_tab, double* __restrict__ tab) {
+    const int t = blockIdx.x;
+    if (t >= n_tab) return;
+    const int pair = tab_pair[t];
+    const int s = pair / f.A, a = pair % f.A;
+    const QParams q = qparams_of(f, s, a);
+    double* out = tab + 3 * tab_off[t];
+    for (int n = threadIdx.x; n < tab_len[t]; n += blockDim.x) {
+        const double sr = (double)serv_rate(q, n + 1);
+        const Recip r = make_recip(sr);
+        out[3 * n + 0] = sr;
+        out[3 * n + 1] = r.yh;
+        out[3 * n + 2] = r.yl;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: candidate grid.
+// ---------------------------------------------------------------------------
+struct CellCols {
+    uint8_t* flags;
+    float *ttft, *itl, *rho, *throughput;
+};
+struct GridArgs {
+    DevFleet f;
+    const int* batch;        // [B]
+    const int* batch_order;  // [B] indices into batch, descending batch size
+    const int* replicas;     // [R]
+    int B, R;
+    const double* tab;       // shared head tables
+    const long long* pair_tab_off;  // [S*A] entry offset of the pair's table (-1: none)
+    Cand* partials;          // [S * B * n_chunks]
+    int n_chunks;
+    unsigned* counter;
+    unsigned n_items;
+    CellCols cells;
+    int* fb_count;           // cells that need the stored-vector fallback
+    long long* fb_cells;
+    int fb_cap;
+};
+
+__device__ __forceinline__ void eval_grid_cell_tail(const DevFleet& f, int s, int a, int b, int r, float rate,
+                                                    float rmax, const QParams& q, const ModelStats& st, Cand& c,
+                                                    Metrics& m) {
+    m = metrics_from(q, b, st);
+    const float slo_ttft = f.srv_slo_ttft[s], slo_itl = f.srv_slo_itl[s];
+    bool feas = (slo_ttft == 0.0f || m.ttft <= slo_ttft) && (slo_itl == 0.0f || m.avg_token_time <= slo_itl) &&
+                (r >= f.srv_min_replicas[s]);
+    if (f.srv_slo_tps[s] > 0.0f) {  // Size's stability margin (queueanalyzer.go:231-234)
+        const float lim = __fmul_rn(__fdiv_rn(rmax, 1000.0f), __fsub_rn(1.0f, 0.1f));
+        feas = feas && (__fdiv_rn(rate, 1000.0f) <= lim);
+    }
+    c = cand_nil();
+    if (feas) {
+        const long long total = (long long)num_instances(f, f.srv_model[s], a) * (long long)r;
+        c.feasible = 1;
+        c.acc = a;
+        c.replicas = r;
+        c.batch = b;
+        c.cost = __fmul_rn(f.acc_cost[a], (float)total);
+        c.value = penalty_of(f, s, c);
+        c.itl = m.avg_token_time;
+        c.ttft = m.ttft;
+        c.rho = m.rho;
+        c.max_rate = __fdiv_rn(rmax, 1000.0f);
+    }
+}
+
+__global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
+    const DevFleet& f = g.f;
+    const int lane = threadIdx.x & 31;
+    const int AR = f.A * g.R;
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(g.counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= g.n_items) break;
+        const int chunk = item % g.n_chunks;
+        const unsigned t = item / g.n_chunks;
+        const int s = t % f.S;
+        const int bi = g.batch_order[t / f.S];
+        const int b = g.batch[bi];
+        const int idx = chunk * 32 + lane;
+        const bool in_range = idx < AR;
+        const int a = in_range ? idx / g.R : 0;
+        const int ri = in_range ? idx % g.R : 0;
+        const int r = g.replicas[ri];
+        const long long cell = (((long long)s * f.A + a) * g.B + bi) * g.R + ri;
+
+        Cand c = cand_nil();
+        Metrics m;
+        m.ttft = m.avg_token_time = m.rho = m.throughput = 0.0f;
+        int ok = 0;
+        const long long toff = in_range ? g.pair_tab_off[s * f.A + a] : -1;
+        if (toff >= 0) {  // pair passes the gates and carries load
+            const double* tab = g.tab + 3 * toff;
+            const int N = b, K = b + b * f.ratio;
+            Recip tail;
+            tail.b = tab[3 * (b - 1)];
+            tail.yh = tab[3 * (b - 1) + 1];
+            tail.yl = tab[3 * (b - 1) + 2];
+            const float rmax = rate_max_of((float)tail.b);
+            const float rate = __fdiv_rn(total_rate_of(f, s), (float)r);
+            // Analyze: queueanalyzer.go:135-150 (K >= 2 so the model is always valid)
+            if (!(rate <= 0.0f) && !(rate > rmax) && K >= 2) {
+                const float lambda = __fdiv_rn(rate, 1000.0f);
+                ModelStats st;
+                const int rc = solve_model<TAB_SHARED>(tab, 0, N, K, lambda, tail, st);
+                if (rc == kSolveOk) {
+                    ok = 1;
+                    const QParams q = qparams_of(f, s, a);
+                    eval_grid_cell_tail(f, s, a, b, r, rate, rmax, q, st, c, m);
+                } else {
+                    const int k = atomicAdd(g.fb_count, 1);
+                    if (k < g.fb_cap) g.fb_cells[k] = cell;
+                }
+            }
+        }
+        if (in_range) {
+            if (g.cells.flags) g.cells.flags[cell] = (uint8_t)(ok | (c.feasible << 1));
+            if (g.cells.ttft) g.cells.ttft[cell] = m.ttft;
+            if (g.cells.itl) g.cells.itl[cell] = m.avg_token_time;
+            if (g.cells.rho) g.cells.rho[cell] = m.rho;
+            if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
+        }
+        c = cand_warp_min(c);
+        if (lane == 0) g.partials[((size_t)s * g.B + bi) * g.n_chunks + chunk] = c;
+    }
+}
+
+// Stored-vector re-run of bailed cells. One thread per slot; slot k handles cells
+// k, k + n_slots, ...  scratch per slot: (Kmax + 1) doubles then Nmax floats.
+__global__ void grid_fallback(GridArgs g, double* scratch, size_t slot_doubles, int Kmax, Cand* fb_cands,
+                              int* fb_status) {
+    const DevFleet& f = g.f;
+    const int n_slots = gridDim.x * blockDim.x;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = *g.fb_count;
+    if (n > g.fb_cap) n = g.fb_cap;
+    double* p = scratch + (size_t)slot * slot_doubles;
+    float* sr = (float*)(p + Kmax + 1);  // servRate copy lives behind the p[0..Kmax] vector
+    for (int k = slot; k < n; k += n_slots) {
+        const long long cell = g.fb_cells[k];
+        const int ri = (int)(cell % g.R);
+        const int bi = (int)((cell / g.R) % g.B);
+        const int a = (int)((cell / ((long long)g.R * g.B)) % f.A);
+        const int s = (int)(cell / ((long long)g.R * g.B * f.A));
+        const int b = g.batch[bi], r = g.replicas[ri];
+        const double* tab = g.tab + 3 * g.pair_tab_off[s * f.A + a];
+        for (int i = 0; i < b; ++i) sr[i] = (float)tab[3 * i];
+        const float rmax = rate_max_of(sr[b - 1]);
+        const float rate = __fdiv_rn(total_rate_of(f, s), (float)r);
+        const float lambda = __fdiv_rn(rate, 1000.0f);
+        ModelStats st;
+        Cand c = cand_nil();
+        Metrics m;
+        m.ttft = m.avg_token_time = m.rho = m.throughput = 0.0f;
+        int ok = 0;
+        const int rc = solve_stored(p, sr, b, b + b * f.ratio, lambda, st);
+        if (rc == 0) {
+            ok = 1;
+            const QParams q = qparams_of(f, s, a);
+            eval_grid_cell_tail(f, s, a, b, r, rate, rmax, q, st, c, m);
+        } else {
+            atomicExch(fb_status, rc);
+        }
+        if (g.cells.flags) g.cells.flags[cell] = (uint8_t)(ok | (c.feasible << 1));
+        if (g.cells.ttft) g.cells.ttft[cell] = m.ttft;
+        if (g.cells.itl) g.cells.itl[cell] = m.avg_token_time;
+        if (g.cells.rho) g.cells.rho[cell] = m.rho;
+        if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
+        // the record's owner travels in `feasible` as server id + 1 (0 = infeasible)
+        c.feasible = c.feasible ? (s + 1) : 0;
+        fb_cands[k] = c;
+    }
+}
+
+// K3: per-server argmin.  One CTA per server: strided scan of the server's partials,
+// warp-shuffle reduction, cross-warp reduction staged through shared memory.
+__global__ void __launch_bounds__(128) grid_finalize(GridArgs g, const Cand* fb_cands, AllocCols winners) {
+    const DevFleet& f = g.f;
+    const int s = blockIdx.x;
+    const int per_server = g.B * g.n_chunks;
+    const Cand* part = g.partials + (size_t)s * per_server;
+    Cand best = cand_nil();
+    for (int i = threadIdx.x; i < per_server; i += blockDim.x) {
+        const Cand c = part[i];
+        if (cand_better(c, best)) best = c;
+    }
+    // zero-traffic servers: the reference's zeroLoadAllocation per candidate accelerator
+    for (int a = threadIdx.x; a < f.A; a += blockDim.x) {
+        if (pair_class(f, s, a, true) == PAIR_ZERO) {
+            Cand c = zero_load_alloc(f, s, a);
+            c.value = penalty_of(f, s, c);
+            if (cand_better(c, best)) best = c;
+        }
+    }
+    // stored-vector fallback records of this server
+    int nfb = *g.fb_count;
+    if (nfb > g.fb_cap) nfb = g.fb_cap;
+    for (int i = threadIdx.x; i < nfb; i += blockDim.x) {
+        Cand c = fb_cands[i];
+        if (c.feasible == s + 1) {
+            c.feasible = 1;
+            if (cand_better(c, best)) best = c;
+        }
+    }
+    best = cand_warp_min(best);
+    __shared__ Cand sm[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sm[warp] = best;
+    __syncthreads();
+    if (warp == 0) {
+        Cand c = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : cand_nil();
+        c = cand_warp_min(c);
+        if (lane == 0) store_cand(winners, s, c);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1: size candidates (CreateAllocation).
+// ---------------------------------------------------------------------------
+
+// float32 servRate columns: group gidx holds 32 consecutive candidates of the sorted
+// list; element n of lane l at ltab[group_off[gidx] + n*32 + l].
+__global__ void build_lane_tables(DevFleet f, const int* __restrict__ cand_pair, const int* __restrict__ cand_N,
+                                  int n_cand, const long long* __restrict__ group_off, float* __restrict__ ltab) {
+    const int gidx = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int j = gidx * 32 + lane;
+    const bool live = j < n_cand;
+    const int pair = live ? cand_pair[j] : 0;
+    const int N = live ? cand_N[j] : 0;
+    const int Ng = cand_N[gidx * 32];  // sorted descending: the first lane has the largest N
+    QParams q;
+    if (live) q = qparams_of(f, pair / f.A, pair % f.A);
+    float* out = ltab + group_off[gidx];
+    for (int n = threadIdx.x >> 5; n < Ng; n += blockDim.x >> 5) {
+        out[(size_t)n * 32 + lane] = (live && n < N) ? serv_rate(q, n + 1) : 1.0f;
+    }
+}
+
+// Solver policies: a solver evaluates Model.Solve(lambda, 1) and reports bail-outs.
+struct LaneSolver {  // streaming solve on the lane's float32 column
+    const float* col;
+    int N, K;
+    Recip tail;
+    int bail;
+    __device__ __forceinline__ int solve(float lambda, ModelStats& st) {
+        const int rc = solve_model<TAB_LANE>(col, 32, N, K, lambda, tail, st);
+        if (rc != kSolveOk) bail = 1;
+        return rc;
+    }
+};
+struct StoredSolver {  // stored-vector fallback
+    double* p;
+    const float* sr;
+    int N, K;
+    int bail;
+    __device__ __forceinline__ int solve(float lambda, ModelStats& st) {
+        const int rc = solve_stored(p, sr, N, K, lambda, st);
+        if (rc != 0) bail = rc;
+        return rc;
+    }
+};
+
+// EvalTTFT / EvalITL (queueanalyzer.go:270-290) + BinarySearch (utils.go:26-70).
+// which = 0: TTFT, 1: ITL.  Returns 0 ok (xstar, ind), 2 eval error / bail.
+template <class Solver>
+__device__ int eval_target(Solver& sv, const QParams& q, int which, float x, float& y) {
+    ModelStats st;
+    if (sv.solve(x, st) != 0) return 2;
+    const float eff = effective_concurrency(q, st.avg_serv_time, sv.N);
+    if (which == 0)
+        y = __fadd_rn(st.avg_wait_time, prefill_time(q, eff));
+    else
+        y = decode_time(q, eff);
+    return 0;
+}
+template <class Solver>
+__device__ int binary_search(Solver& sv, const QParams& q, int which, float xmin, float xmax, float ytarget,
+                             float& xstar, int& ind) {
+    xstar = 0.0f;
+    ind = 0;
+    if (xmin > xmax) return 1;
+    float y0, y1;
+    if (eval_target(sv, q, which, xmin, y0)) return 2;
+    if (within_tolerance(y0, ytarget, 1e-6f)) { xstar = xmin; return 0; }
+    if (eval_target(sv, q, which, xmax, y1)) return 2;
+    if (within_tolerance(y1, ytarget, 1e-6f)) { xstar = xmax; return 0; }
+    const bool increasing = y0 < y1;
+    if ((increasing && ytarget < y0) || (!increasing && ytarget > y0)) { xstar = xmin; ind = -1; return 0; }
+    if ((increasing && ytarget > y1) || (!increasing && ytarget < y1)) { xstar = xmax; ind = 1; return 0; }
+    float xs = 0.0f, ys = 0.0f;
+    for (int it = 0; it < 100; ++it) {
+        xs = __fmul_rn(0.5f, __fadd_rn(xmin, xmax));
+        if (eval_target(sv, q, which, xs, ys)) return 2;
+        if (within_tolerance(ys, ytarget, 1e-6f)) break;
+        if ((increasing && ytarget < ys) || (!increasing && ytarget > ys))
+            xmax = xs;
+        else
+            xmin = xs;
+    }
+    xstar = xs;
+    return 0;
+}
+
+// Analyze (queueanalyzer.go:134-174) -> 0 ok.
+template <class Solver>
+__device__ int analyze(Solver& sv, const QParams& q, float rmax, float rate, Metrics& m) {
+    if (rate <= 0.0f) return 1;
+    if (rate > rmax) return 2;
+    ModelStats st;
+    if (sv.solve(__fdiv_rn(rate, 1000.0f), st) != 0) return 3;
+    m = metrics_from(q, sv.N, st);
+    return 0;
+}
+
+// CreateAllocation under load (allocation.go:77-163); value = cost.
+// s1 / sN = servRate[0] / servRate[N-1] (float32).
+template <class Solver>
+__device__ Cand create_allocation(const DevFleet& f, int s, int a, Solver& sv, float s1, float sN) {
+    Cand out = cand_nil();
+    if (sv.K < 2) return out;  // a model with K <= 1 is never valid (queuemodel.go:31, stale rho = 1)
+    const QParams q = qparams_of(f, s, a);
+    const float rmin = rate_min_of(s1), rmax = rate_max_of(sN);
+    const float slo_ttft = f.srv_slo_ttft[s], slo_itl = f.srv_slo_itl[s], slo_tps = f.srv_slo_tps[s];
+    if (slo_itl < 0.0f || slo_ttft < 0.0f || slo_tps < 0.0f) return out;  // TargetPerf.check :322-329
+    const float lambda_min = __fdiv_rn(rmin, 1000.0f), lambda_max = __fdiv_rn(rmax, 1000.0f);
+    int ind = 0;
+    float l_ttft = lambda_max, l_itl = lambda_max, l_tps = lambda_max;
+    if (slo_ttft > 0.0f) {  // queueanalyzer.go:205-215
+        const int err = binary_search(sv, q, 0, lambda_min, lambda_max, slo_ttft, l_ttft, ind);
+        if (ind < 0 || err != 0) return out;
+    }
+    if (slo_itl > 0.0f) {  // :218-228
+        const int err = binary_search(sv, q, 1, lambda_min, lambda_max, slo_itl, l_itl, ind);
+        if (ind < 0 || err != 0) return out;
+    }
+    if (slo_tps > 0.0f) l_tps = __fmul_rn(lambda_max, __fsub_rn(1.0f, 0.1f));  // :231-234
+    const float lambda = go_minf(go_minf(l_ttft, l_itl), l_tps);
+    Metrics m;
+    if (analyze(sv, q, rmax, __fmul_rn(lambda, 1000.0f), m) != 0) return out;  // :237-241
+    const float rate_star = m.throughput;
+
+    const float total_rate = total_rate_of(f, s);  // allocation.go:134-141
+    long long nrep = go_f64_to_int(ceil(__ddiv_rn((double)total_rate, (double)rate_star)));
+    const long long min_rep = f.srv_min_replicas[s];
+    if (nrep < min_rep) nrep = min_rep;
+    const long long total = (long long)num_instances(f, f.srv_model[s], a) * nrep;  // :144-145
+    const float cost = __fmul_rn(f.acc_cost[a], (float)total);
+    const float rate = __fdiv_rn(total_rate, (float)nrep);  // :148-153
+    if (analyze(sv, q, rmax, rate, m) != 0) return out;
+    out.feasible = 1;
+    out.acc = a;
+    out.replicas = (int)nrep;
+    out.batch = sv.N;
+    out.cost = cost;
+    out.value = cost;
+    out.itl = m.avg_token_time;
+    out.ttft = m.ttft;
+    out.rho = m.rho;
+    out.max_rate = __fdiv_rn(rate_star, 1000.0f);
+    return out;
+}
+
+struct SizeArgs {
+    DevFleet f;
+    const int* cand_pair;  // [n_cand] pair ids sorted by descending N
+    const int* cand_N;     // [n_cand]
+    int n_cand;
+    const float* ltab;
+    const long long* group_off;
+    AllocCols cand;        // [S*A]
+    int* fb_count;
+    int* fb_list;          // candidate indices that bailed
+    int fb_cap;
+};
+
+__global__ void __launch_bounds__(128) size_kernel(SizeArgs g) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.n_cand) return;
+    const DevFleet& f = g.f;
+    const int pair = g.cand_pair[j];
+    const int s = pair / f.A, a = pair % f.A;
+    LaneSolver sv;
+    sv.N = g.cand_N[j];
+    sv.K = sv.N + sv.N * f.ratio;
+    sv.col = g.ltab + g.group_off[j >> 5] + (j & 31);
+    sv.bail = 0;
+    const float s1 = sv.col[0], sN = sv.col[(size_t)(sv.N - 1) * 32];
+    sv.tail = make_recip((double)sN);
+    Cand c = create_allocation(f, s, a, sv, s1, sN);
+    if (sv.bail) {
+        const int k = atomicAdd(g.fb_count, 1);
+        if (k < g.fb_cap) g.fb_list[k] = j;
+        c = cand_nil();
+    }
+    store_cand(g.cand, pair, c);
+}
+
+// Stored-vector re-run of bailed candidates (slot k handles list entries k, k+n_slots, ..).
+__global__ void size_fallback(SizeArgs g, double* scratch, size_t slot_doubles, int Kmax, int* fb_status) {
+    const DevFleet& f = g.f;
+    const int n_slots = gridDim.x * blockDim.x;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = *g.fb_count;
+    if (n > g.fb_cap) n = g.fb_cap;
+    double* p = scratch + (size_t)slot * slot_doubles;
+    float* sr = (float*)(p + Kmax + 1);
+    for (int k = slot; k < n; k += n_slots) {
+        const int j = g.fb_list[k];
+        const int pair = g.cand_pair[j];
+        const int s = pair / f.A, a = pair % f.A;
+        StoredSolver sv;
+        sv.N = g.cand_N[j];
+        sv.K = sv.N + sv.N * f.ratio;
+        sv.p = p;
+        sv.sr = sr;
+        sv.bail = 0;
+        const QParams q = qparams_of(f, s, a);
+        for (int i = 0; i < sv.N; ++i) sr[i] = serv_rate(q, i + 1);
+        for (int i = 0; i <= sv.K; ++i) p[i] = 0.0;
+        Cand c = create_allocation(f, s, a, sv, sr[0], sr[sv.N - 1]);
+        if (sv.bail) {
+            atomicExch(fb_status, sv.bail);
+            c = cand_nil();
+        }
+        store_cand(g.cand, pair, c);
+    }
+}
+
+// nil and zero-load candidates (everything the size kernel does not own).
+__global__ void trivial_kernel(DevFleet f, AllocCols cand) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= f.S * f.A) return;
+    const int s = pair / f.A, a = pair % f.A;
+    const int cls = pair_class(f, s, a, true);
+    if (cls == PAIR_LOAD) return;
+    Cand c = cand_nil();
+    if (cls == PAIR_ZERO) c = zero_load_alloc(f, s, a);
+    store_cand(cand, pair, c);
+}
+
+// Server.Calculate's value (server.go:60-63) + SolveUnlimited (solver.go:63-79):
+// one thread per server; strict '<' from MaxFloat32, lowest accelerator id wins ties.
+__global__ void unlimited_kernel(DevFleet f, AllocCols cand, AllocCols winners) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= f.S) return;
+    float min_val = 3.40282346638528859811704183484516925440e+38f;
+    Cand best = cand_nil();
+    for (int a = 0; a < f.A; ++a) {
+        const size_t i = (size_t)s * f.A + a;
+        if (!cand.feasible[i]) continue;
+        Cand c = load_cand(cand, i);
+        c.value = penalty_of(f, s, c);
+        cand.value[i] = c.value;
+        if (c.value < min_val) {
+            min_val = c.value;
+            best = c;
+        }
+    }
+    store_cand(winners, s, best);
+}
+
+// ---------------------------------------------------------------------------
+// Latency sweep: warp = 32 consecutive rates of one (server, acc) pair.
+// ---------------------------------------------------------------------------
+struct SweepArgs {
+    DevFleet f;
+    const int* pair_list;  // pairs sorted by descending N
+    const int* pair_N;     // N per entry of pair_list
+    const long long* tab_off;  // shared-table entry offset per entry of pair_list
+    const double* tab;
+    int n_pairs, n_rates, n_chunks;
+    unsigned* counter;
+    uint8_t* valid;
+    float *rate, *ttft, *itl, *throughput, *rho;
+    int* fb_count;
+};
+
+__global__ void __launch_bounds__(256) sweep_kernel(SweepArgs g) {
+    const DevFleet& f = g.f;
+    const int lane = threadIdx.x & 31;
+    const unsigned n_items = (unsigned)g.n_pairs * g.n_chunks;
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(g.counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int e = item / g.n_chunks, chunk = item % g.n_chunks;
+        const int pair = g.pair_list[e];
+        const int s = pair / f.A, a = pair % f.A;
+        const int N = g.pair_N[e], K = N + N * f.ratio;
+        const double* tab = g.tab + 3 * g.tab_off[e];
+        Recip tail;
+        tail.b = tab[3 * (N - 1)];
+        tail.yh = tab[3 * (N - 1) + 1];
+        tail.yl = tab[3 * (N - 1) + 2];
+        const float rmin = rate_min_of((float)tab[0]), rmax = rate_max_of((float)tail.b);
+        const int i = chunk * 32 + lane;
+        if (i < g.n_rates) {
+        const float hi = __fmul_rn(rmax, 0.999f);
+        const float span = __fsub_rn(hi, rmin);
+        const float frac = g.n_rates > 1 ? __fdiv_rn((float)i, (float)(g.n_rates - 1)) : 0.0f;
+        const float rate = __fadd_rn(rmin, __fmul_rn(span, frac));
+        const size_t o = (size_t)pair * g.n_rates + i;
+        g.rate[o] = rate;
+        uint8_t ok = 0;
+        Metrics m;
+        m.ttft = m.avg_token_time = m.rho = m.throughput = 0.0f;
+        if (!(rate <= 0.0f) && !(rate > rmax) && K >= 2) {
+            ModelStats st;
+            const QParams q = qparams_of(f, s, a);
+            if (solve_model<TAB_SHARED>(tab, 0, N, K, __fdiv_rn(rate, 1000.0f), tail, st) == kSolveOk) {
+                m = metrics_from(q, N, st);
+                ok = 1;
+            } else {
+                atomicAdd(g.fb_count, 1);
+            }
+        }
+        g.valid[o] = ok;
+        g.ttft[o] = m.ttft;
+        g.itl[o] = m.avg_token_time;
+        g.throughput[o] = m.throughput;
+        g.rho[o] = m.rho;
+        }
+    }
+}
+
+}  // namespace wva

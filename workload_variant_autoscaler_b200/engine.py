@@ -1,0 +1,145 @@
+"""Host-side mirror of the reference's optimizer interface over the C ABI.
+
+``Engine`` plays the role of ``core.System`` + ``manager.Manager`` +
+``solver.Optimizer`` for the hot path (pkg/manager/manager.go:13-27,
+pkg/solver/optimizer.go:24-35, pkg/core/system.go:303-319): hand it the fleet
+(``config.SystemSpec`` packed as a :class:`Fleet`), get candidate allocations
+(``Server.Calculate``) and the per-server solution (``GenerateSolution``).  All compute
+happens in the CUDA library; nothing here touches the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, _lib
+from ._abi import Allocs
+from .fleet import Fleet, Grid
+
+
+class WvaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"wva error {code}: {msg}")
+        self.code = code
+
+
+class Engine:
+    """One engine per GPU (one process per GPU in multi-GPU runs)."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        rc = self._L.wva_create(C.byref(h), device)
+        if rc != 0:
+            raise WvaError(rc, self._L.wva_strerror(rc).decode() + " (the CUDA path has no CPU fallback)")
+        self._h = h
+        self._fleet = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.wva_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise WvaError(rc, f"{self._L.wva_strerror(rc).decode()}: {self._L.wva_last_error(self._h).decode()}")
+
+    # -- reference-shaped calls --------------------------------------------
+    def analyze(self, fleet: Fleet) -> Allocs:
+        """``Server.Calculate`` for every server -> candidates [S*A] (pkg/core/server.go:55-67)."""
+        cand = Allocs(fleet.n_servers * fleet.n_acc)
+        fc, cc = fleet.as_c(), cand.as_c()
+        self._check(self._L.wva_analyze(self._h, C.byref(fc), C.byref(cc)))
+        return cand
+
+    def solve(self, fleet: Fleet, want_candidates: bool = True):
+        """``Manager.Optimize`` + ``GenerateSolution`` -> (candidates [S*A] | None, winners [S])."""
+        cand = Allocs(fleet.n_servers * fleet.n_acc) if want_candidates else None
+        win = Allocs(fleet.n_servers)
+        fc, wc = fleet.as_c(), win.as_c()
+        cc = cand.as_c() if cand is not None else None
+        self._check(self._L.wva_solve(self._h, C.byref(fc), C.byref(cc) if cc is not None else None, C.byref(wc)))
+        return cand, win
+
+    def grid_solve(self, fleet: Fleet, grid: Grid, want_cells: bool = False):
+        """Full (server x acc x batch x replica) grid -> (cells | None, winners [S])."""
+        n = fleet.n_servers * fleet.n_acc * int(grid.batch.size) * int(grid.replicas.size)
+        win = Allocs(fleet.n_servers)
+        cells = None
+        cc = None
+        if want_cells:
+            cells = {"flags": np.zeros(n, np.uint8)}
+            for k in ("ttft", "itl", "rho", "throughput"):
+                cells[k] = np.zeros(n, np.float32)
+            cc = _abi.CellsC(*[_abi.ptr(cells[k]) for k in ("flags", "ttft", "itl", "rho", "throughput")])
+        fc, gc, wc = fleet.as_c(), grid.as_c(), win.as_c()
+        self._check(self._L.wva_grid_solve(self._h, C.byref(fc), C.byref(gc), C.byref(cc) if cc is not None else None,
+                                           C.byref(wc)))
+        return cells, win
+
+    def sweep(self, fleet: Fleet, n_rates: int) -> dict:
+        n = fleet.n_servers * fleet.n_acc * n_rates
+        out = {"valid": np.zeros(n, np.uint8)}
+        for k in ("rate", "ttft", "itl", "throughput", "rho"):
+            out[k] = np.zeros(n, np.float32)
+        oc = _abi.SweepOutC(*[_abi.ptr(out[k]) for k in ("valid", "rate", "ttft", "itl", "throughput", "rho")])
+        fc = fleet.as_c()
+        self._check(self._L.wva_sweep(self._h, C.byref(fc), n_rates, C.byref(oc)))
+        return out
+
+    # -- streaming reconcile ------------------------------------------------
+    def upload(self, fleet: Fleet):
+        fc = fleet.as_c()
+        self._check(self._L.wva_upload(self._h, C.byref(fc)))
+        self._fleet = fleet
+
+    def update_load(self, arrival_rpm=None, in_tokens=None, out_tokens=None):
+        a = np.ascontiguousarray(arrival_rpm, np.float32) if arrival_rpm is not None else None
+        i = np.ascontiguousarray(in_tokens, np.int32) if in_tokens is not None else None
+        o = np.ascontiguousarray(out_tokens, np.int32) if out_tokens is not None else None
+        self._check(self._L.wva_update_load(self._h, _abi.ptr(a) if a is not None else None,
+                                            _abi.ptr(i) if i is not None else None,
+                                            _abi.ptr(o) if o is not None else None))
+
+    def resolve(self, want_candidates: bool = False):
+        f = self._fleet
+        cand = Allocs(f.n_servers * f.n_acc) if want_candidates else None
+        win = Allocs(f.n_servers)
+        wc = win.as_c()
+        cc = cand.as_c() if cand is not None else None
+        self._check(self._L.wva_resolve(self._h, C.byref(cc) if cc is not None else None, C.byref(wc)))
+        return cand, win
+
+    # -- device-resident variants (multi-GPU driver, bench) -------------------
+    def grid_solve_device(self, grid: Grid, winners_dev: _abi.AllocsC):
+        gc = grid.as_c()
+        self._check(self._L.wva_grid_solve_device(self._h, C.byref(gc), C.byref(winners_dev)))
+
+    def resolve_device(self, winners_dev: _abi.AllocsC):
+        self._check(self._L.wva_resolve_device(self._h, C.byref(winners_dev)))
+
+    def synchronize(self):
+        self._check(self._L.wva_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.wva_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.wva_launch_count(self._h))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(self._L.wva_last_kernel_ms(self._h))
+
+    @property
+    def last_device_ms(self) -> float:
+        return float(self._L.wva_last_device_ms(self._h))
