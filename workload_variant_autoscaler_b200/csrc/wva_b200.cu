@@ -605,7 +605,7 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
             CK(h->d_tab_pair.ensure(sizeof(int) * n_tab));
             CK(h->d_tab_off.ensure(sizeof(long long) * n_tab));
             CK(h->d_tab_len.ensure(sizeof(int) * n_tab));
-            CK(h->d_tab.ensure(sizeof(double) * 3 * (size_t)off));
+            CK(h->d_tab.ensure(sizeof(double) * 4 * (size_t)off));
             CK(cudaMemcpyAsync(h->d_tab_pair.p, tab_pair.data(), sizeof(int) * n_tab, cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(h->d_tab_off.p, tab_off.data(), sizeof(long long) * n_tab, cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(h->d_tab_len.p, tab_len.data(), sizeof(int) * n_tab, cudaMemcpyHostToDevice, h->stream));
@@ -634,12 +634,12 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     g.R = R;
     g.tab = (const double*)h->d_tab.p;
     g.pair_tab_off = (const long long*)h->d_pair_tab.p;
-    g.n_chunks = (A * R + 31) / 32;
-    const size_t n_part = (size_t)S * B * std::max(g.n_chunks, 1);
+    g.n_chunks = (B + 31) / 32;
+    const size_t n_part = (size_t)S * A * R * std::max(g.n_chunks, 1);
     CK(h->d_partials.ensure(sizeof(Cand) * std::max<size_t>(n_part, 1)));
     g.partials = (Cand*)h->d_partials.p;
     g.counter = (unsigned*)h->d_ctrl.p + CTRL_COUNTER;
-    const unsigned long long n_items = (unsigned long long)S * B * g.n_chunks;
+    const unsigned long long n_items = (unsigned long long)S * A * R * g.n_chunks;
     if (n_items > 0xfffffff0ull) return h->fail(WVA_ERR_UNSUPPORTED, "grid too large for one call");
     g.n_items = (unsigned)n_items;
     plan->n_cells = (size_t)S * A * B * R;
@@ -976,7 +976,7 @@ int wva_sweep(wva_handle* h, const wva_fleet* fleet, int32_t n_rates, wva_sweep_
         CK(h->d_tab_pair.ensure(sizeof(int) * n));
         CK(h->d_tab_off.ensure(sizeof(long long) * n));
         CK(h->d_tab_len.ensure(sizeof(int) * n));
-        CK(h->d_tab.ensure(sizeof(double) * 3 * (size_t)off));
+        CK(h->d_tab.ensure(sizeof(double) * 4 * (size_t)off));
         CK(cudaMemcpyAsync(h->d_tab_pair.p, pairs.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_tab_off.p, offs.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_tab_len.p, lens.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));

@@ -124,6 +124,16 @@ constexpr unsigned kHiSumHi = WVA_HI(620);
 // the running sum (same summation order as :93-105); pass 2 re-runs the identical
 // recurrence (identical roundings, so identical p[n]), normalises each p[n] by the sum
 // (:108-112) and accumulates sum(i*p[i]) and sumP in the reference's order (:47-55).
+//
+// Exact early termination.  Once the chain is past its mode (lambda below every
+// remaining service rate, so p is non-increasing from there on) and p[j] has dropped
+// below 2^-78 * min(p[0], p[1]), every later term is a no-op in all three float64
+// accumulations of the reference: sum >= p[0] = 1, sumP >= p[0]/sum, and
+// sum(i*p[i]/sum) >= p[1]/sum while i < 2^23, so each remaining addend is below half an
+// ulp of its accumulator; and float32(p[K]/sum) < 2^-25 makes 1 - float32(p[K]) == 1.
+// Skipping those steps therefore changes no output bit (proof in DESIGN.md).  A chain
+// that underflows to exactly 0 ends the same way.
+//
 // The overflow-rescale branches (:84-89, :96-104) cannot be reproduced without the
 // stored vector; when a value leaves the safe window the solve reports kSolveBail and
 // the caller re-runs the cell on the stored-vector fallback (solve_stored below).
@@ -135,127 +145,155 @@ struct ModelStats {  // queuemodel.go:10-19 + mm1kmodel.go:15 + mm1modelstatedep
 };
 
 // Head tables.  TAB_SHARED: one table per (server, accelerator) pair, read at the same
-// address by every lane of a warp: 3 doubles per n (servRate, yh, yl).  TAB_LANE: one
-// float32 servRate column per lane, element n at tab[n * stride] (coalesced across the
-// warp); the head then uses the generic IEEE division.
+// address by the lanes of a warp: 4 doubles per n {servRate[n], yh, yl, min(servRate[n..])}.
+// TAB_LANE: one float32 servRate column per lane, element n at tab[n * stride] (coalesced
+// across the warp) plus n_mono, the index from which the column is non-decreasing; the
+// head then uses the generic IEEE division.
 enum { TAB_SHARED = 0, TAB_LANE = 1 };
 
 template <int TAB>
 __device__ __forceinline__ double head_rate(const void* tab, int stride, int n) {
-    if (TAB == TAB_SHARED) return ((const double*)tab)[3 * n];
+    if (TAB == TAB_SHARED) return ((const double*)tab)[4 * n];
     return (double)((const float*)tab)[(size_t)n * stride];
 }
 template <int TAB>
 __device__ __forceinline__ double head_step_fast(const void* tab, int stride, int n, double a) {
     if (TAB == TAB_SHARED) {
-        const double* t = (const double*)tab + 3 * n;
+        const double2* t = (const double2*)((const double*)tab + 4 * n);
+        const double2 t0 = t[0];
         Recip r;
-        r.b = t[0];
-        r.yh = t[1];
-        r.yl = t[2];
+        r.b = t0.x;
+        r.yh = t0.y;
+        r.yl = ((const double*)tab)[4 * n + 2];
         return div_recip(a, r);
     }
     return __ddiv_rn(a, (double)((const float*)tab)[(size_t)n * stride]);
+}
+// Is p non-increasing from state j (< N-1) on?  True when lambda is clearly below every
+// service rate the remaining steps divide by.
+template <int TAB>
+__device__ __forceinline__ bool mono_from(const void* tab, int stride, int n_mono, int j, double lam) {
+    if (TAB == TAB_SHARED)
+        return (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(((const double*)tab)[4 * j + 3]);
+    return j >= n_mono &&
+           (unsigned)__double2hiint(lam) < (unsigned)__double2hiint((double)((const float*)tab)[(size_t)j * stride]);
 }
 
 // Returns kSolveOk / kSolveBail.  N = len(servRate), K = occupancy upper bound (>= 2),
 // lam = float64(lambda), tail = servRate[N-1] with its reciprocal.
 template <int TAB>
-__device__ __noinline__ int solve_model(const void* tab, int stride, int N, int K, float lambda, const Recip& tail,
-                                        ModelStats& st) {
+__device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono, int N, int K, float lambda,
+                                        const Recip& tail, ModelStats& st) {
     const double lam = (double)lambda;
     if (!in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail.b, kHiRateLo, kHiRateHi)) return kSolveBail;
     const int nh = N - 1;  // steps n < nh read servRate[n] from the table; the rest use the tail
+    // in the tail p is non-increasing iff lambda < servRate[N-1] (with a margin for rounding)
+    const bool tail_mono = (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tail.b);
+
+    // ---- p[1] and the negligibility threshold --------------------------------------
+    double p = (nh > 0) ? head_step_fast<TAB>(tab, stride, 0, lam) : div_recip(lam, tail);  // RN(1*lambda) = lambda
+    if (!(p >= 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
+    const double p1 = p;
+    unsigned thr_hi = 0;  // early exit when hi(p) < thr_hi; 0 disables it
+    if (K < (1 << 23)) thr_hi = (unsigned)__double2hiint(__dmul_rn(fmin(1.0, p1), 0x1p-78));
 
     // ---- pass 1: normalising sum ------------------------------------------------
-    double p = 1.0, sum = 1.0;
+    double sum = __dadd_rn(1.0, p);
+    int j_end = K + 1;  // first state index that is skipped (K + 1: nothing skipped)
     {
-        int n = 0;
-        bool zero = false;
-        for (; n < nh; ++n) {
+        int n = 1;  // p holds p[n]
+        bool ended = false;
+        for (; !ended && n < nh; ++n) {
             if (in_window(p, kHiPLo, kHiPHi)) {
                 p = head_step_fast<TAB>(tab, stride, n, __dmul_rn(p, lam));
             } else {
-                if (p == 0.0) { zero = true; break; }
+                if (p == 0.0) { ended = true; j_end = n + 1; break; }
                 if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
                 p = __ddiv_rn(__dmul_rn(p, lam), head_rate<TAB>(tab, stride, n));
             }
             sum = __dadd_rn(sum, p);
+            if ((unsigned)__double2hiint(p) < thr_hi) {
+                const int j = n + 1;
+                if (j >= nh ? tail_mono : mono_from<TAB>(tab, stride, n_mono, j, lam)) {
+                    ended = true;
+                    j_end = j + 1;
+                    break;
+                }
+            }
         }
-        if (!zero) {
+        if (!ended) {
+            const unsigned thr_tail = tail_mono ? thr_hi : 0u;
 #pragma unroll 4
             for (; n < K; ++n) {
                 if (in_window(p, kHiPLo, kHiPHi)) {
                     p = div_recip(__dmul_rn(p, lam), tail);
                 } else {
-                    if (p == 0.0) break;
+                    if (p == 0.0) { j_end = n + 1; break; }
                     if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
                     p = __ddiv_rn(__dmul_rn(p, lam), tail.b);
                 }
                 sum = __dadd_rn(sum, p);
+                if ((unsigned)__double2hiint(p) < thr_tail) { j_end = n + 2; break; }
             }
         }
     }
     if (!in_window(sum, kHiSumLo, kHiSumHi)) return kSolveBail;
+    if (j_end > K + 1) j_end = K + 1;
 
-    // ---- pass 2: normalise, accumulate -----------------------------------------
+    // ---- pass 2: normalise, accumulate states 1 .. j_end-1 ----------------------------
+    // (pass 1 established that states >= j_end contribute nothing)
     const Recip z = make_recip(sum);
     const double pn0 = z.yh;  // p[0]/sum = RN(1/sum)
-    double acc = 0.0, sum_p = pn0, in_serv = 0.0, pn = pn0, di = 1.0;
+    double acc = 0.0, sum_p = pn0, pn = 0.0, di = 1.0;
     const double dN = (double)N;
-    // p[1] from p[0] = 1: RN(1*lambda) = lambda
-    p = (nh > 0) ? head_step_fast<TAB>(tab, stride, 0, lam) : div_recip(lam, tail);
+    p = p1;
     int i = 1;
-    bool done = false;
-    // states 1..N: also feed sumP and capture avgNumInServers at i == N (:50-54)
-    for (; i <= N; ++i) {
+    const int iA = (N < j_end - 1) ? N : j_end - 1;  // states that also feed sumP
+    for (; i <= iA; ++i) {
         const bool fast = in_window(p, kHiPLo, kHiPHi);
         if (fast) {
             pn = div_recip(p, z);
         } else {
-            if (p == 0.0) { pn = 0.0; done = true; break; }
-            if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
+            if (p == 0.0) { pn = 0.0; i = j_end; break; }
             pn = __ddiv_rn(p, sum);
         }
         acc = __dadd_rn(acc, __dmul_rn(di, pn));
         sum_p = __dadd_rn(sum_p, pn);
         di = __dadd_rn(di, 1.0);
-        if (i < K) {
+        if (i + 1 < j_end) {
             const double a = __dmul_rn(p, lam);
-            if (fast) {
+            if (fast)
                 p = (i < nh) ? head_step_fast<TAB>(tab, stride, i, a) : div_recip(a, tail);
-            } else {
+            else
                 p = __ddiv_rn(a, (i < nh) ? head_rate<TAB>(tab, stride, i) : tail.b);
-            }
         }
     }
-    // i == N was reached (or every later p is exactly 0, which leaves acc and sumP unchanged)
-    in_serv = __dadd_rn(acc, __dmul_rn(__dsub_rn(1.0, sum_p), dN));
-    if (!done) {
+    // avgNumInServers is captured at i == N (:50-54); when the chain ended before N the
+    // remaining updates of acc and sumP are no-ops, so the current values are the ones
+    const double in_serv = __dadd_rn(acc, __dmul_rn(__dsub_rn(1.0, sum_p), dN));
 #pragma unroll 2
-        for (; i <= K; ++i) {
-            const bool fast = in_window(p, kHiPLo, kHiPHi);
-            if (fast) {
-                pn = div_recip(p, z);
-            } else {
-                if (p == 0.0) { pn = 0.0; break; }
-                if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
-                pn = __ddiv_rn(p, sum);
-            }
-            acc = __dadd_rn(acc, __dmul_rn(di, pn));
-            di = __dadd_rn(di, 1.0);
-            if (i < K) {
-                const double a = __dmul_rn(p, lam);
-                p = fast ? div_recip(a, tail) : __ddiv_rn(a, tail.b);
-            }
+    for (; i < j_end; ++i) {
+        const bool fast = in_window(p, kHiPLo, kHiPHi);
+        if (fast) {
+            pn = div_recip(p, z);
+        } else {
+            if (p == 0.0) { pn = 0.0; break; }
+            pn = __ddiv_rn(p, sum);
+        }
+        acc = __dadd_rn(acc, __dmul_rn(di, pn));
+        di = __dadd_rn(di, 1.0);
+        if (i + 1 < j_end) {
+            const double a = __dmul_rn(p, lam);
+            p = fast ? div_recip(a, tail) : __ddiv_rn(a, tail.b);
         }
     }
-    // pn now holds p[K] (0 if the chain died out)
+    // p[K]/sum: pn if the chain ran to K, otherwise below 2^-77 (so 1 - float32(.) == 1)
+    const double pnK = (j_end == K + 1) ? pn : 0.0;
 
     // ---- float32 tail: mm1modelstatedependent.go:56-66 --------------------------
     st.avg_num_in_servers = (float)in_serv;
     const float avg_num_in_system = (float)acc;
-    st.throughput = __fmul_rn(lambda, __fsub_rn(1.0f, (float)pn));
+    st.throughput = __fmul_rn(lambda, __fsub_rn(1.0f, (float)pnK));
     st.avg_resp_time = __fdiv_rn(avg_num_in_system, st.throughput);
     st.avg_serv_time = __fdiv_rn(st.avg_num_in_servers, st.throughput);
     float w = __fsub_rn(st.avg_resp_time, st.avg_serv_time);

@@ -170,7 +170,8 @@ __device__ __forceinline__ Cand zero_load_alloc(const DevFleet& f, int s, int a)
 }
 
 // ---------------------------------------------------------------------------
-// Shared head tables: entry n (0-based) of pair t = {servRate[n], yh, yl} as doubles.
+// Shared head tables: entry n (0-based) of table t = {servRate[n], yh, yl, min(servRate[n..len-1])}
+// as doubles (32 B, so a lane needs two 16 B loads per head step).
 // ---------------------------------------------------------------------------
 __global__ void build_pair_tables(DevFleet f, const int* __restrict__ tab_pair, const long long* __restrict__ tab_off,
                                   const int* __restrict__ tab_len, int n_tab, double* __restrict__ tab) {
@@ -179,13 +180,23 @@ __global__ void build_pair_tables(DevFleet f, const int* __restrict__ tab_pair, 
     const int pair = tab_pair[t];
     const int s = pair / f.A, a = pair % f.A;
     const QParams q = qparams_of(f, s, a);
-    double* out = tab + 3 * tab_off[t];
-    for (int n = threadIdx.x; n < tab_len[t]; n += blockDim.x) {
+    double* out = tab + 4 * tab_off[t];
+    const int len = tab_len[t];
+    for (int n = threadIdx.x; n < len; n += blockDim.x) {
         const double sr = (double)serv_rate(q, n + 1);
         const Recip r = make_recip(sr);
-        out[3 * n + 0] = sr;
-        out[3 * n + 1] = r.yh;
-        out[3 * n + 2] = r.yl;
+        out[4 * n + 0] = sr;
+        out[4 * n + 1] = r.yh;
+        out[4 * n + 2] = r.yl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // suffix minimum (NaN-poisoning: a NaN rate disables early exit)
+        double m = out[4 * (len - 1)];
+        for (int n = len - 1; n >= 0; --n) {
+            const double v = out[4 * n];
+            m = (v < m) ? v : ((v >= m) ? m : 0.0);
+            out[4 * n + 3] = m;
+        }
     }
 }
 
@@ -204,7 +215,7 @@ struct GridArgs {
     int B, R;
     const double* tab;       // shared head tables
     const long long* pair_tab_off;  // [S*A] entry offset of the pair's table (-1: none)
-    Cand* partials;          // [S * B * n_chunks]
+    Cand* partials;          // [S * A * R * n_chunks], n_chunks = ceil(B / 32)
     int n_chunks;
     unsigned* counter;
     unsigned n_items;
@@ -241,24 +252,30 @@ __device__ __forceinline__ void eval_grid_cell_tail(const DevFleet& f, int s, in
     }
 }
 
+// Work item = (batch chunk, replica level, server, accelerator): the 32 lanes of a warp take
+// 32 consecutive batch sizes of the descending-sorted batch list for ONE (server,
+// accelerator, replica) triple.  All lanes then share lambda and the service-rate table, and
+// their chains run in lock-step through the common head, so they end (early exit or K)
+// within a few steps of each other: no lane waits long for a slower neighbour.
 __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const DevFleet& f = g.f;
     const int lane = threadIdx.x & 31;
-    const int AR = f.A * g.R;
     for (;;) {
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(g.counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= g.n_items) break;
-        const int chunk = item % g.n_chunks;
-        const unsigned t = item / g.n_chunks;
+        // item = ((chunk * R + ri) * S + s) * A + a  (largest batch sizes, then highest load first)
+        const int a = item % f.A;
+        unsigned t = item / f.A;
         const int s = t % f.S;
-        const int bi = g.batch_order[t / f.S];
+        t /= f.S;
+        const int ri = t % g.R;
+        const int chunk = t / g.R;
+        const int rank = chunk * 32 + lane;
+        const bool in_range = rank < g.B;
+        const int bi = g.batch_order[in_range ? rank : 0];
         const int b = g.batch[bi];
-        const int idx = chunk * 32 + lane;
-        const bool in_range = idx < AR;
-        const int a = in_range ? idx / g.R : 0;
-        const int ri = in_range ? idx % g.R : 0;
         const int r = g.replicas[ri];
         const long long cell = (((long long)s * f.A + a) * g.B + bi) * g.R + ri;
 
@@ -266,21 +283,21 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
         Metrics m;
         m.ttft = m.avg_token_time = m.rho = m.throughput = 0.0f;
         int ok = 0;
-        const long long toff = in_range ? g.pair_tab_off[s * f.A + a] : -1;
-        if (toff >= 0) {  // pair passes the gates and carries load
-            const double* tab = g.tab + 3 * toff;
+        const long long toff = g.pair_tab_off[s * f.A + a];
+        if (toff >= 0 && in_range) {  // pair passes the gates and carries load
+            const double* tab = g.tab + 4 * toff;
             const int N = b, K = b + b * f.ratio;
             Recip tail;
-            tail.b = tab[3 * (b - 1)];
-            tail.yh = tab[3 * (b - 1) + 1];
-            tail.yl = tab[3 * (b - 1) + 2];
+            tail.b = tab[4 * (b - 1)];
+            tail.yh = tab[4 * (b - 1) + 1];
+            tail.yl = tab[4 * (b - 1) + 2];
             const float rmax = rate_max_of((float)tail.b);
             const float rate = __fdiv_rn(total_rate_of(f, s), (float)r);
             // Analyze: queueanalyzer.go:135-150 (K >= 2 so the model is always valid)
             if (!(rate <= 0.0f) && !(rate > rmax) && K >= 2) {
                 const float lambda = __fdiv_rn(rate, 1000.0f);
                 ModelStats st;
-                const int rc = solve_model<TAB_SHARED>(tab, 0, N, K, lambda, tail, st);
+                const int rc = solve_model<TAB_SHARED>(tab, 0, 0, N, K, lambda, tail, st);
                 if (rc == kSolveOk) {
                     ok = 1;
                     const QParams q = qparams_of(f, s, a);
@@ -299,7 +316,7 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
             if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
         }
         c = cand_warp_min(c);
-        if (lane == 0) g.partials[((size_t)s * g.B + bi) * g.n_chunks + chunk] = c;
+        if (lane == 0) g.partials[(((size_t)s * f.A + a) * g.R + ri) * g.n_chunks + chunk] = c;
     }
 }
 
@@ -321,8 +338,8 @@ __global__ void grid_fallback(GridArgs g, double* scratch, size_t slot_doubles, 
         const int a = (int)((cell / ((long long)g.R * g.B)) % f.A);
         const int s = (int)(cell / ((long long)g.R * g.B * f.A));
         const int b = g.batch[bi], r = g.replicas[ri];
-        const double* tab = g.tab + 3 * g.pair_tab_off[s * f.A + a];
-        for (int i = 0; i < b; ++i) sr[i] = (float)tab[3 * i];
+        const double* tab = g.tab + 4 * g.pair_tab_off[s * f.A + a];
+        for (int i = 0; i < b; ++i) sr[i] = (float)tab[4 * i];
         const float rmax = rate_max_of(sr[b - 1]);
         const float rate = __fdiv_rn(total_rate_of(f, s), (float)r);
         const float lambda = __fdiv_rn(rate, 1000.0f);
@@ -355,7 +372,7 @@ __global__ void grid_fallback(GridArgs g, double* scratch, size_t slot_doubles, 
 __global__ void __launch_bounds__(128) grid_finalize(GridArgs g, const Cand* fb_cands, AllocCols winners) {
     const DevFleet& f = g.f;
     const int s = blockIdx.x;
-    const int per_server = g.B * g.n_chunks;
+    const int per_server = f.A * g.R * g.n_chunks;
     const Cand* part = g.partials + (size_t)s * per_server;
     Cand best = cand_nil();
     for (int i = threadIdx.x; i < per_server; i += blockDim.x) {
@@ -418,11 +435,11 @@ __global__ void build_lane_tables(DevFleet f, const int* __restrict__ cand_pair,
 // Solver policies: a solver evaluates Model.Solve(lambda, 1) and reports bail-outs.
 struct LaneSolver {  // streaming solve on the lane's float32 column
     const float* col;
-    int N, K;
+    int N, K, n_mono;
     Recip tail;
     int bail;
     __device__ __forceinline__ int solve(float lambda, ModelStats& st) {
-        const int rc = solve_model<TAB_LANE>(col, 32, N, K, lambda, tail, st);
+        const int rc = solve_model<TAB_LANE>(col, 32, n_mono, N, K, lambda, tail, st);
         if (rc != kSolveOk) bail = 1;
         return rc;
     }
@@ -565,6 +582,10 @@ __global__ void __launch_bounds__(128) size_kernel(SizeArgs g) {
     sv.bail = 0;
     const float s1 = sv.col[0], sN = sv.col[(size_t)(sv.N - 1) * 32];
     sv.tail = make_recip((double)sN);
+    sv.n_mono = sv.N - 1;  // index from which the service-rate column is non-decreasing
+    for (int n = sv.N - 2; n >= 0; --n) {
+        if (sv.col[(size_t)n * 32] <= sv.col[(size_t)(n + 1) * 32]) sv.n_mono = n; else break;
+    }
     Cand c = create_allocation(f, s, a, sv, s1, sN);
     if (sv.bail) {
         const int k = atomicAdd(g.fb_count, 1);
@@ -667,11 +688,11 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepArgs g) {
         const int pair = g.pair_list[e];
         const int s = pair / f.A, a = pair % f.A;
         const int N = g.pair_N[e], K = N + N * f.ratio;
-        const double* tab = g.tab + 3 * g.tab_off[e];
+        const double* tab = g.tab + 4 * g.tab_off[e];
         Recip tail;
-        tail.b = tab[3 * (N - 1)];
-        tail.yh = tab[3 * (N - 1) + 1];
-        tail.yl = tab[3 * (N - 1) + 2];
+        tail.b = tab[4 * (N - 1)];
+        tail.yh = tab[4 * (N - 1) + 1];
+        tail.yl = tab[4 * (N - 1) + 2];
         const float rmin = rate_min_of((float)tab[0]), rmax = rate_max_of((float)tail.b);
         const int i = chunk * 32 + lane;
         if (i < g.n_rates) {
@@ -687,7 +708,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepArgs g) {
         if (!(rate <= 0.0f) && !(rate > rmax) && K >= 2) {
             ModelStats st;
             const QParams q = qparams_of(f, s, a);
-            if (solve_model<TAB_SHARED>(tab, 0, N, K, __fdiv_rn(rate, 1000.0f), tail, st) == kSolveOk) {
+            if (solve_model<TAB_SHARED>(tab, 0, 0, N, K, __fdiv_rn(rate, 1000.0f), tail, st) == kSolveOk) {
                 m = metrics_from(q, N, st);
                 ok = 1;
             } else {
