@@ -137,9 +137,9 @@ struct wva_handle {
     uint64_t grid_epoch = ~0ull;
     std::vector<int> grid_batch, grid_replicas;
     int grid_Bmax = 0, grid_n_tab = 0;
-    DevBuf d_grid_lists, d_pair_tab, d_tab_pair, d_tab_off, d_tab_len, d_tab, d_partials;
+    DevBuf d_grid_lists, d_pair_tab, d_tab_pair, d_tab_off, d_tab_len, d_tab, d_ls, d_sort, d_best;
     // shared
-    DevBuf d_cand_block, d_win_block, d_ctrl, d_fb_list, d_fb_cands, d_scratch, d_cells, d_sweep;
+    DevBuf d_cand_block, d_win_block, d_ctrl, d_fb_list, d_scratch, d_cells, d_sweep;
     PinBuf out_stage;
 
     int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -159,6 +159,11 @@ struct wva_handle {
     } while (0)
 
 namespace {
+
+__global__ void fill_int(int* p, size_t n, int v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 
 // control block on the device: a handful of ints
 enum { CTRL_COUNTER = 0, CTRL_FB_COUNT = 1, CTRL_FB_STATUS = 2, CTRL_INTS = 8 };
@@ -547,9 +552,24 @@ int validate_grid(wva_handle* h, const wva_grid* g) {
 struct GridPlan {
     GridArgs args;
     size_t n_cells;
-    int n_tab;
+    int n_blocks;
     int Bmax;
 };
+
+// Per-cell columns kept on the device for every grid solve: flags + ttft/itl/rho (+ throughput
+// when the caller asked for the cell table).
+int ensure_cells(wva_handle* h, GridPlan& plan, bool want_throughput) {
+    const size_t nc = std::max<size_t>(plan.n_cells, 1);
+    const size_t bytes = align_up(nc) + 4 * align_up(4 * nc);
+    CK(h->d_cells.ensure(bytes));
+    char* p = (char*)h->d_cells.p;
+    plan.args.cells.flags = (uint8_t*)p;
+    plan.args.cells.ttft = (float*)(p + align_up(nc));
+    plan.args.cells.itl = (float*)(p + align_up(nc) + align_up(4 * nc));
+    plan.args.cells.rho = (float*)(p + align_up(nc) + 2 * align_up(4 * nc));
+    plan.args.cells.throughput = want_throughput ? (float*)(p + align_up(nc) + 3 * align_up(4 * nc)) : nullptr;
+    return WVA_OK;
+}
 
 int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     const HostFleet& hf = h->hf;
@@ -561,51 +581,52 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     const int n_pairs = S * A;
     int Bmax = 1;
     for (int i = 0; i < B; ++i) Bmax = std::max(Bmax, grid->batch[i]);
-    // device lists: batch[B], order[B], replicas[R]
-    const size_t lists_bytes = sizeof(int) * (size_t)(2 * B + R + 1);
-    CK(h->d_grid_lists.ensure(lists_bytes));
-    CK(h->d_pair_tab.ensure(sizeof(long long) * std::max(n_pairs, 1)));
-    // pageable sources: cudaMemcpyAsync has consumed them by the time it returns
-    std::vector<int> lists, tab_pair, tab_len;
-    std::vector<long long> pair_tab, tab_off;
+    // device lists: batch[B], batch_rank[B], rank_to_bi[B], replicas[R]
+    CK(h->d_grid_lists.ensure(sizeof(int) * (size_t)(3 * B + R + 1)));
+    CK(h->d_pair_tab.ensure((sizeof(long long) + sizeof(int)) * std::max(n_pairs, 1)));
+    long long* d_pair_off = (long long*)h->d_pair_tab.p;
+    int* d_pair_idx = (int*)(d_pair_off + std::max(n_pairs, 1));
     if (!same_grid) {
+        // pageable sources: cudaMemcpyAsync has consumed them by the time it returns
+        std::vector<int> lists(3 * B + R + 1), tab_pair, tab_len, pair_idx(std::max(n_pairs, 1), -1);
+        std::vector<long long> pair_tab(std::max(n_pairs, 1), -1), tab_off;
         h->grid_batch.assign(grid->batch, grid->batch + B);
         h->grid_replicas.assign(grid->replicas, grid->replicas + R);
-        lists.resize(2 * B + R + 1);
         std::vector<int> order(B);
         std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return grid->batch[x] > grid->batch[y]; });
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return grid->batch[x] < grid->batch[y]; });
         for (int i = 0; i < B; ++i) {
             lists[i] = grid->batch[i];
-            lists[B + i] = order[i];
+            lists[B + order[i]] = i;      // batch_rank[bi]
+            lists[2 * B + i] = order[i];  // rank_to_bi[rank]
         }
-        for (int i = 0; i < R; ++i) lists[2 * B + i] = grid->replicas[i];
-        if (2 * B + R > 0)
-            CK(cudaMemcpyAsync(h->d_grid_lists.p, lists.data(), sizeof(int) * (size_t)(2 * B + R), cudaMemcpyHostToDevice,
+        for (int i = 0; i < R; ++i) lists[3 * B + i] = grid->replicas[i];
+        if (3 * B + R > 0)
+            CK(cudaMemcpyAsync(h->d_grid_lists.p, lists.data(), sizeof(int) * (size_t)(3 * B + R), cudaMemcpyHostToDevice,
                                h->stream));
         // shared service-rate tables for every pair that carries load
-        pair_tab.assign(std::max(n_pairs, 1), -1);
-        tab_pair.clear();
-        tab_off.clear();
-        tab_len.clear();
         long long off = 0;
         for (int s = 0; s < S; ++s)
             for (int a = 0; a < A; ++a)
                 if (hf.pair_class(s, a, true) == PAIR_LOAD && hf.srv_out_tokens[s] >= 1) {
                     pair_tab[(size_t)s * A + a] = off;
+                    pair_idx[(size_t)s * A + a] = (int)tab_pair.size();
                     tab_pair.push_back(s * A + a);
                     tab_off.push_back(off);
                     tab_len.push_back(Bmax);
                     off += Bmax;
                 }
         const int n_tab = (int)tab_pair.size();
-        CK(cudaMemcpyAsync(h->d_pair_tab.p, pair_tab.data(), sizeof(long long) * std::max(n_pairs, 1),
-                           cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d_pair_off, pair_tab.data(), sizeof(long long) * std::max(n_pairs, 1), cudaMemcpyHostToDevice,
+                           h->stream));
+        CK(cudaMemcpyAsync(d_pair_idx, pair_idx.data(), sizeof(int) * std::max(n_pairs, 1), cudaMemcpyHostToDevice,
+                           h->stream));
         if (n_tab) {
             CK(h->d_tab_pair.ensure(sizeof(int) * n_tab));
             CK(h->d_tab_off.ensure(sizeof(long long) * n_tab));
             CK(h->d_tab_len.ensure(sizeof(int) * n_tab));
             CK(h->d_tab.ensure(sizeof(double) * 4 * (size_t)off));
+            CK(h->d_ls.ensure(sizeof(float) * ((size_t)off + n_tab)));
             CK(cudaMemcpyAsync(h->d_tab_pair.p, tab_pair.data(), sizeof(int) * n_tab, cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(h->d_tab_off.p, tab_off.data(), sizeof(long long) * n_tab, cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(h->d_tab_len.p, tab_len.data(), sizeof(int) * n_tab, cudaMemcpyHostToDevice, h->stream));
@@ -620,7 +641,7 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
         build_pair_tables<<<h->grid_n_tab, 128, 0, h->stream>>>(h->df, (const int*)h->d_tab_pair.p,
                                                                 (const long long*)h->d_tab_off.p,
                                                                 (const int*)h->d_tab_len.p, h->grid_n_tab,
-                                                                (double*)h->d_tab.p);
+                                                                (double*)h->d_tab.p, (float*)h->d_ls.p);
         h->launches++;
         CK(cudaGetLastError());
     }
@@ -628,25 +649,37 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     g = GridArgs{};
     g.f = h->df;
     g.batch = (const int*)h->d_grid_lists.p;
-    g.batch_order = g.batch + B;
-    g.replicas = g.batch + 2 * B;
+    g.batch_rank = g.batch + B;
+    g.rank_to_bi = g.batch + 2 * B;
+    g.replicas = g.batch + 3 * B;
     g.B = B;
     g.R = R;
     g.tab = (const double*)h->d_tab.p;
-    g.pair_tab_off = (const long long*)h->d_pair_tab.p;
-    g.n_chunks = (B + 31) / 32;
-    const size_t n_part = (size_t)S * A * R * std::max(g.n_chunks, 1);
-    CK(h->d_partials.ensure(sizeof(Cand) * std::max<size_t>(n_part, 1)));
-    g.partials = (Cand*)h->d_partials.p;
-    g.counter = (unsigned*)h->d_ctrl.p + CTRL_COUNTER;
-    const unsigned long long n_items = (unsigned long long)S * A * R * g.n_chunks;
-    if (n_items > 0xfffffff0ull) return h->fail(WVA_ERR_UNSUPPORTED, "grid too large for one call");
-    g.n_items = (unsigned)n_items;
-    plan->n_cells = (size_t)S * A * B * R;
+    g.ls = (const float*)h->d_ls.p;
+    g.pair_tab_off = d_pair_off;
+    g.pair_tab_idx = d_pair_idx;
+    const unsigned long long n_cells = (unsigned long long)S * A * B * R;
+    if (n_cells > 0xfffffff0ull) return h->fail(WVA_ERR_UNSUPPORTED, "grid too large for one call (>= 2^32 cells)");
+    g.n_cells = (long long)n_cells;
+    plan->n_cells = (size_t)n_cells;
+    plan->n_blocks = (int)((n_cells + kSortChunk - 1) / kSortChunk);
+    const size_t nc = std::max<size_t>(plan->n_cells, 1);
+    // sort workspace: keys u8 | order u32 | block histograms | class bases
+    const size_t ws = align_up(nc) + align_up(4 * nc) + align_up(4 * (size_t)std::max(plan->n_blocks, 1) * kClasses) +
+                      align_up(4 * (kClasses + 1));
+    CK(h->d_sort.ensure(ws));
+    char* w = (char*)h->d_sort.p;
+    g.keys = (uint8_t*)w;
+    g.order = (unsigned*)(w + align_up(nc));
+    g.block_hist = (unsigned*)(w + align_up(nc) + align_up(4 * nc));
+    g.class_base = (unsigned*)(w + align_up(nc) + align_up(4 * nc) +
+                               align_up(4 * (size_t)std::max(plan->n_blocks, 1) * kClasses));
+    const size_t n_best = std::max<size_t>((size_t)S * A * R, 1);
+    CK(h->d_best.ensure(sizeof(int) * n_best));
+    g.best_rank = (int*)h->d_best.p;
     g.fb_count = (int*)h->d_ctrl.p + CTRL_FB_COUNT;
-    g.fb_cap = (int)std::min<size_t>(std::max<size_t>(plan->n_cells, 1), (size_t)1 << 22);
+    g.fb_cap = (int)std::min<size_t>(nc, (size_t)1 << 22);
     CK(h->d_fb_list.ensure(sizeof(long long) * g.fb_cap));
-    CK(h->d_fb_cands.ensure(sizeof(Cand) * g.fb_cap));
     g.fb_cells = (long long*)h->d_fb_list.p;
     plan->Bmax = Bmax;
     return WVA_OK;
@@ -659,26 +692,26 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
     int Kmax;
     int rc = ensure_scratch(h, plan.Bmax, hf.tun.max_queue_to_batch_ratio, &slot_doubles, &Kmax);
     if (rc) return rc;
+    const size_t n_best = (size_t)hf.S * hf.A * g.R;
     CK(cudaEventRecord(h->ev_k0, h->stream));
-    if (g.n_items > 0) {
-        int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_kernel, 256, 0));
-        per_sm = std::max(1, std::min(per_sm, 8));
-        const unsigned warps_needed = g.n_items;
-        unsigned blocks = (unsigned)(h->sm_count * per_sm);
-        blocks = std::min(blocks, (warps_needed + 7) / 8);
+    if (plan.n_cells > 0) {
+        CK(cudaMemsetAsync(g.cells.flags, 0, plan.n_cells, h->stream));
+        fill_int<<<(unsigned)((n_best + 255) / 256), 256, 0, h->stream>>>(g.best_rank, n_best, INT_MAX);
+        grid_estimate<<<plan.n_blocks, 256, 0, h->stream>>>(g);
+        grid_scan<<<1, 256, 0, h->stream>>>(g, plan.n_blocks);
+        grid_scatter<<<plan.n_blocks, 256, 0, h->stream>>>(g);
+        const unsigned blocks = (unsigned)((plan.n_cells + 255) / 256);
         grid_kernel<<<blocks, 256, 0, h->stream>>>(g);
-        h->launches++;
+        h->launches += 5;
     }
     CK(cudaEventRecord(h->ev_k1, h->stream));
-    if (g.n_items > 0) {
+    if (plan.n_cells > 0) {
         grid_fallback<<<kFbBlocks, kFbThreads, 0, h->stream>>>(g, (double*)h->d_scratch.p, slot_doubles, Kmax,
-                                                               (Cand*)h->d_fb_cands.p,
                                                                (int*)h->d_ctrl.p + CTRL_FB_STATUS);
         h->launches++;
     }
     if (hf.S > 0) {
-        grid_finalize<<<hf.S, 128, 0, h->stream>>>(g, (const Cand*)h->d_fb_cands.p, winners);
+        grid_finalize<<<hf.S, 128, 0, h->stream>>>(g, winners);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -741,8 +774,8 @@ void wva_destroy(wva_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->arena, &h->d_cand_pair, &h->d_cand_N, &h->d_group_off, &h->d_ltab, &h->d_grid_lists,
-                      &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_partials,
-                      &h->d_cand_block, &h->d_win_block, &h->d_ctrl, &h->d_fb_list, &h->d_fb_cands, &h->d_scratch,
+                      &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_ls, &h->d_sort, &h->d_best,
+                      &h->d_cand_block, &h->d_win_block, &h->d_ctrl, &h->d_fb_list, &h->d_scratch,
                       &h->d_cells, &h->d_sweep};
     for (DevBuf* b : bufs) b->release();
     h->stage.release();
@@ -864,6 +897,8 @@ int wva_grid_solve_device(wva_handle* h, const wva_grid* grid, wva_allocs* winne
     GridPlan plan;
     rc = prepare_grid(h, grid, &plan);
     if (rc) return rc;
+    rc = ensure_cells(h, plan, false);
+    if (rc) return rc;
     CK(cudaEventRecord(h->ev_d0, h->stream));
     rc = enqueue_grid(h, plan, cols_from_abi(winners_dev));
     if (rc) return rc;
@@ -887,21 +922,13 @@ int wva_grid_solve(wva_handle* h, const wva_fleet* fleet, const wva_grid* grid, 
     const Block bw = block_layout(hf.S);
     CK(h->d_win_block.ensure(bw.bytes + 16));
     const AllocCols dw = block_cols(h->d_win_block.p, bw);
-    // optional per-cell table: flags u8 + 4 float columns
+    // per-cell columns live on the device for every solve; they travel to the host only on request
     const size_t nc = plan.n_cells;
     const bool want_cells = cells && (cells->flags || cells->ttft || cells->itl || cells->rho || cells->throughput);
-    size_t cell_bytes = 0;
-    if (want_cells) {
-        cell_bytes = align_up(nc) + 4 * align_up(4 * nc);
-        CK(h->d_cells.ensure(cell_bytes));
-        char* p = (char*)h->d_cells.p;
-        plan.args.cells.flags = (uint8_t*)p;
-        plan.args.cells.ttft = (float*)(p + align_up(nc));
-        plan.args.cells.itl = (float*)(p + align_up(nc) + align_up(4 * nc));
-        plan.args.cells.rho = (float*)(p + align_up(nc) + 2 * align_up(4 * nc));
-        plan.args.cells.throughput = (float*)(p + align_up(nc) + 3 * align_up(4 * nc));
-        CK(cudaMemsetAsync(p, 0, cell_bytes, h->stream));
-    }
+    rc = ensure_cells(h, plan, want_cells && cells->throughput);
+    if (rc) return rc;
+    if (want_cells && nc)  // cells that are never analysed must read back as 0
+        CK(cudaMemsetAsync(h->d_cells.p, 0, align_up(nc) + 4 * align_up(4 * nc), h->stream));
     CK(cudaEventRecord(h->ev_d0, h->stream));
     rc = enqueue_grid(h, plan, dw);
     if (rc) return rc;
@@ -982,7 +1009,7 @@ int wva_sweep(wva_handle* h, const wva_fleet* fleet, int32_t n_rates, wva_sweep_
         CK(cudaMemcpyAsync(h->d_tab_len.p, lens.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
         h->grid_epoch = ~0ull;  // the shared-table buffers now hold sweep tables
         build_pair_tables<<<n, 128, 0, h->stream>>>(h->df, (const int*)h->d_tab_pair.p, (const long long*)h->d_tab_off.p,
-                                                    (const int*)h->d_tab_len.p, n, (double*)h->d_tab.p);
+                                                    (const int*)h->d_tab_len.p, n, (double*)h->d_tab.p, nullptr);
         h->launches++;
         SweepArgs g{};
         g.f = h->df;

@@ -151,24 +151,6 @@ struct ModelStats {  // queuemodel.go:10-19 + mm1kmodel.go:15 + mm1modelstatedep
 // head then uses the generic IEEE division.
 enum { TAB_SHARED = 0, TAB_LANE = 1 };
 
-template <int TAB>
-__device__ __forceinline__ double head_rate(const void* tab, int stride, int n) {
-    if (TAB == TAB_SHARED) return ((const double*)tab)[4 * n];
-    return (double)((const float*)tab)[(size_t)n * stride];
-}
-template <int TAB>
-__device__ __forceinline__ double head_step_fast(const void* tab, int stride, int n, double a) {
-    if (TAB == TAB_SHARED) {
-        const double2* t = (const double2*)((const double*)tab + 4 * n);
-        const double2 t0 = t[0];
-        Recip r;
-        r.b = t0.x;
-        r.yh = t0.y;
-        r.yl = ((const double*)tab)[4 * n + 2];
-        return div_recip(a, r);
-    }
-    return __ddiv_rn(a, (double)((const float*)tab)[(size_t)n * stride]);
-}
 // Is p non-increasing from state j (< N-1) on?  True when lambda is clearly below every
 // service rate the remaining steps divide by.
 template <int TAB>
@@ -179,8 +161,36 @@ __device__ __forceinline__ bool mono_from(const void* tab, int stride, int n_mon
            (unsigned)__double2hiint(lam) < (unsigned)__double2hiint((double)((const float*)tab)[(size_t)j * stride]);
 }
 
+// Table access for one step: the reciprocal triple of servRate[min(n, N-1)].
+template <int TAB>
+__device__ __forceinline__ Recip step_recip(const void* tab, int stride, int n, int nh, const Recip& tail) {
+    if (TAB == TAB_SHARED) {
+        if (n < nh) {
+            const double2 t0 = *(const double2*)((const double*)tab + 4 * n);
+            Recip r;
+            r.b = t0.x;
+            r.yh = t0.y;
+            r.yl = ((const double*)tab)[4 * n + 2];
+            return r;
+        }
+        return tail;
+    }
+    Recip r = tail;
+    if (n < nh) r.b = (double)((const float*)tab)[(size_t)n * stride];
+    return r;
+}
+// One recurrence step p[n] -> p[n+1] on the fast path (p inside the window).
+template <int TAB>
+__device__ __forceinline__ double step_fast(const void* tab, int stride, int n, int nh, const Recip& tail, double a) {
+    const Recip r = step_recip<TAB>(tab, stride, n, nh, tail);
+    if (TAB == TAB_LANE && n < nh) return __ddiv_rn(a, r.b);  // no reciprocal for per-lane head rates
+    return div_recip(a, r);
+}
+
 // Returns kSolveOk / kSolveBail.  N = len(servRate), K = occupancy upper bound (>= 2),
-// lam = float64(lambda), tail = servRate[N-1] with its reciprocal.
+// tail = servRate[N-1] with its reciprocal.  Every loop is a single per-lane loop (no
+// separate head / tail code paths) so that lanes of a warp that work on different batch
+// sizes stay converged: only the trip count differs between lanes.
 template <int TAB>
 __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono, int N, int K, float lambda,
                                         const Recip& tail, ModelStats& st) {
@@ -191,7 +201,7 @@ __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono,
     const bool tail_mono = (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tail.b);
 
     // ---- p[1] and the negligibility threshold --------------------------------------
-    double p = (nh > 0) ? head_step_fast<TAB>(tab, stride, 0, lam) : div_recip(lam, tail);  // RN(1*lambda) = lambda
+    double p = step_fast<TAB>(tab, stride, 0, nh, tail, lam);  // RN(1*lambda) = lambda
     if (!(p >= 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
     const double p1 = p;
     unsigned thr_hi = 0;  // early exit when hi(p) < thr_hi; 0 disables it
@@ -200,79 +210,35 @@ __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono,
     // ---- pass 1: normalising sum ------------------------------------------------
     double sum = __dadd_rn(1.0, p);
     int j_end = K + 1;  // first state index that is skipped (K + 1: nothing skipped)
-    {
-        int n = 1;  // p holds p[n]
-        bool ended = false;
-        for (; !ended && n < nh; ++n) {
-            if (in_window(p, kHiPLo, kHiPHi)) {
-                p = head_step_fast<TAB>(tab, stride, n, __dmul_rn(p, lam));
-            } else {
-                if (p == 0.0) { ended = true; j_end = n + 1; break; }
-                if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
-                p = __ddiv_rn(__dmul_rn(p, lam), head_rate<TAB>(tab, stride, n));
-            }
-            sum = __dadd_rn(sum, p);
-            if ((unsigned)__double2hiint(p) < thr_hi) {
-                const int j = n + 1;
-                if (j >= nh ? tail_mono : mono_from<TAB>(tab, stride, n_mono, j, lam)) {
-                    ended = true;
-                    j_end = j + 1;
-                    break;
-                }
-            }
+#pragma unroll 2
+    for (int n = 1; n < K; ++n) {  // p holds p[n]
+        if (in_window(p, kHiPLo, kHiPHi)) {
+            p = step_fast<TAB>(tab, stride, n, nh, tail, __dmul_rn(p, lam));
+        } else {
+            if (p == 0.0) { j_end = n + 1; break; }
+            if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
+            p = __ddiv_rn(__dmul_rn(p, lam), step_recip<TAB>(tab, stride, n, nh, tail).b);
         }
-        if (!ended) {
-            const unsigned thr_tail = tail_mono ? thr_hi : 0u;
-#pragma unroll 4
-            for (; n < K; ++n) {
-                if (in_window(p, kHiPLo, kHiPHi)) {
-                    p = div_recip(__dmul_rn(p, lam), tail);
-                } else {
-                    if (p == 0.0) { j_end = n + 1; break; }
-                    if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
-                    p = __ddiv_rn(__dmul_rn(p, lam), tail.b);
-                }
-                sum = __dadd_rn(sum, p);
-                if ((unsigned)__double2hiint(p) < thr_tail) { j_end = n + 2; break; }
+        sum = __dadd_rn(sum, p);
+        if ((unsigned)__double2hiint(p) < thr_hi) {  // p[n+1] is negligible: is the chain past its mode?
+            const int j = n + 1;
+            if (j >= nh ? tail_mono : mono_from<TAB>(tab, stride, n_mono, j, lam)) {
+                j_end = j + 1;
+                break;
             }
         }
     }
     if (!in_window(sum, kHiSumLo, kHiSumHi)) return kSolveBail;
-    if (j_end > K + 1) j_end = K + 1;
 
     // ---- pass 2: normalise, accumulate states 1 .. j_end-1 ----------------------------
     // (pass 1 established that states >= j_end contribute nothing)
     const Recip z = make_recip(sum);
     const double pn0 = z.yh;  // p[0]/sum = RN(1/sum)
-    double acc = 0.0, sum_p = pn0, pn = 0.0, di = 1.0;
-    const double dN = (double)N;
+    double acc = 0.0, sum_p = pn0, pn = 0.0, di = 1.0, acc_at_N = 0.0;
+    bool captured = false;
     p = p1;
-    int i = 1;
-    const int iA = (N < j_end - 1) ? N : j_end - 1;  // states that also feed sumP
-    for (; i <= iA; ++i) {
-        const bool fast = in_window(p, kHiPLo, kHiPHi);
-        if (fast) {
-            pn = div_recip(p, z);
-        } else {
-            if (p == 0.0) { pn = 0.0; i = j_end; break; }
-            pn = __ddiv_rn(p, sum);
-        }
-        acc = __dadd_rn(acc, __dmul_rn(di, pn));
-        sum_p = __dadd_rn(sum_p, pn);
-        di = __dadd_rn(di, 1.0);
-        if (i + 1 < j_end) {
-            const double a = __dmul_rn(p, lam);
-            if (fast)
-                p = (i < nh) ? head_step_fast<TAB>(tab, stride, i, a) : div_recip(a, tail);
-            else
-                p = __ddiv_rn(a, (i < nh) ? head_rate<TAB>(tab, stride, i) : tail.b);
-        }
-    }
-    // avgNumInServers is captured at i == N (:50-54); when the chain ended before N the
-    // remaining updates of acc and sumP are no-ops, so the current values are the ones
-    const double in_serv = __dadd_rn(acc, __dmul_rn(__dsub_rn(1.0, sum_p), dN));
 #pragma unroll 2
-    for (; i < j_end; ++i) {
+    for (int i = 1; i < j_end; ++i) {
         const bool fast = in_window(p, kHiPLo, kHiPHi);
         if (fast) {
             pn = div_recip(p, z);
@@ -282,11 +248,21 @@ __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono,
         }
         acc = __dadd_rn(acc, __dmul_rn(di, pn));
         di = __dadd_rn(di, 1.0);
+        if (i <= N) {
+            sum_p = __dadd_rn(sum_p, pn);
+            if (i == N) { acc_at_N = acc; captured = true; }  // :50-54
+        }
         if (i + 1 < j_end) {
             const double a = __dmul_rn(p, lam);
-            p = fast ? div_recip(a, tail) : __ddiv_rn(a, tail.b);
+            if (fast)
+                p = step_fast<TAB>(tab, stride, i, nh, tail, a);
+            else
+                p = __ddiv_rn(a, step_recip<TAB>(tab, stride, i, nh, tail).b);
         }
     }
+    // when the chain ended before state N the remaining updates of acc and sumP are no-ops
+    if (!captured) acc_at_N = acc;
+    const double in_serv = __dadd_rn(acc_at_N, __dmul_rn(__dsub_rn(1.0, sum_p), (double)N));
     // p[K]/sum: pn if the chain ran to K, otherwise below 2^-77 (so 1 - float32(.) == 1)
     const double pnK = (j_end == K + 1) ? pn : 0.0;
 

@@ -171,10 +171,12 @@ __device__ __forceinline__ Cand zero_load_alloc(const DevFleet& f, int s, int a)
 
 // ---------------------------------------------------------------------------
 // Shared head tables: entry n (0-based) of table t = {servRate[n], yh, yl, min(servRate[n..len-1])}
-// as doubles (32 B, so a lane needs two 16 B loads per head step).
+// as doubles (32 B, two 16 B loads per head step), plus a float column
+// ls[n] = sum_{i<n} log2(servRate[i]) used only to ESTIMATE chain lengths for scheduling.
 // ---------------------------------------------------------------------------
 __global__ void build_pair_tables(DevFleet f, const int* __restrict__ tab_pair, const long long* __restrict__ tab_off,
-                                  const int* __restrict__ tab_len, int n_tab, double* __restrict__ tab) {
+                                  const int* __restrict__ tab_len, int n_tab, double* __restrict__ tab,
+                                  float* __restrict__ ls) {
     const int t = blockIdx.x;
     if (t >= n_tab) return;
     const int pair = tab_pair[t];
@@ -190,7 +192,7 @@ __global__ void build_pair_tables(DevFleet f, const int* __restrict__ tab_pair, 
         out[4 * n + 2] = r.yl;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {  // suffix minimum (NaN-poisoning: a NaN rate disables early exit)
+    if (threadIdx.x == 0) {  // suffix minimum (a NaN rate poisons it to 0 = early exit disabled)
         double m = out[4 * (len - 1)];
         for (int n = len - 1; n >= 0; --n) {
             const double v = out[4 * n];
@@ -198,37 +200,174 @@ __global__ void build_pair_tables(DevFleet f, const int* __restrict__ tab_pair, 
             out[4 * n + 3] = m;
         }
     }
+    if (threadIdx.x == 32 && ls) {  // prefix sum of log2(servRate) (scheduling heuristic only)
+        float* l = ls + tab_off[t] + t;  // len + 1 entries per table
+        double acc = 0.0;
+        for (int n = 0; n <= len; ++n) {
+            l[n] = (float)acc;
+            if (n < len) acc += (double)log2f((float)out[4 * n]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
 // K2: candidate grid.
+//
+//   grid_estimate   per cell: gates + Analyze's rate checks, a cheap log-domain estimate of
+//                   the chain length, an 8-bit length class; per-block class histograms
+//   grid_scan       exclusive scan of the histograms (counting sort, step 2)
+//   grid_scatter    cell ids ordered by descending estimated chain length
+//   grid_kernel     32 cells of (nearly) equal chain length per warp: streaming solve,
+//                   metrics, SLO feasibility, per-cell columns, atomicMin of the smallest
+//                   feasible batch rank per (server, accelerator, replica)
+//   grid_fallback   stored-vector re-run of the rare cells the streaming solve bails on
+//   grid_finalize   per-server argmin (warp shuffle -> shared memory -> winner record)
+//
+// For a fixed (server, accelerator, replica level) the transition penalty and the cost do
+// not depend on the batch size, so the winner among batch sizes is the smallest feasible
+// one; the per-server winner is then the best of the A*R survivors under the order
+// value, cost, replicas, batch, accelerator.
 // ---------------------------------------------------------------------------
 struct CellCols {
-    uint8_t* flags;
+    uint8_t* flags;  // bit0: Analyze ok, bit1: SLO-feasible
     float *ttft, *itl, *rho, *throughput;
 };
+constexpr int kSortChunk = 4096;   // cells per block in the counting sort
+constexpr int kClasses = 256;      // 8-bit length classes; class 255 = not analysable
 struct GridArgs {
     DevFleet f;
     const int* batch;        // [B]
-    const int* batch_order;  // [B] indices into batch, descending batch size
+    const int* batch_rank;   // [B] rank of batch[bi] in ascending (batch, bi) order
+    const int* rank_to_bi;   // [B] inverse of batch_rank
     const int* replicas;     // [R]
     int B, R;
     const double* tab;       // shared head tables
+    const float* ls;         // prefix log2 sums (estimate only)
     const long long* pair_tab_off;  // [S*A] entry offset of the pair's table (-1: none)
-    Cand* partials;          // [S * A * R * n_chunks], n_chunks = ceil(B / 32)
-    int n_chunks;
-    unsigned* counter;
-    unsigned n_items;
-    CellCols cells;
+    const int* pair_tab_idx;        // [S*A] table index (for the ls column)
+    long long n_cells;
+    uint8_t* keys;           // [n_cells] length class
+    unsigned* block_hist;    // [n_blocks * 256]
+    unsigned* class_base;    // [256] (+1: number of analysable cells)
+    unsigned* order;         // [n_cells] cell ids, longest chains first
+    int* best_rank;          // [S*A*R] smallest feasible batch rank (INT_MAX: none)
+    CellCols cells;          // internal per-cell columns (ttft, itl, rho always present)
     int* fb_count;           // cells that need the stored-vector fallback
     long long* fb_cells;
     int fb_cap;
 };
 
-__device__ __forceinline__ void eval_grid_cell_tail(const DevFleet& f, int s, int a, int b, int r, float rate,
-                                                    float rmax, const QParams& q, const ModelStats& st, Cand& c,
-                                                    Metrics& m) {
-    m = metrics_from(q, b, st);
+__device__ __forceinline__ void decode_cell(const GridArgs& g, long long cell, int& s, int& a, int& bi, int& ri) {
+    ri = (int)(cell % g.R);
+    long long t = cell / g.R;
+    bi = (int)(t % g.B);
+    t /= g.B;
+    a = (int)(t % g.f.A);
+    s = (int)(t / g.f.A);
+}
+
+// Estimated number of chain states before exact early termination (scheduling only; any
+// value is correct, a good one makes the 32 lanes of a warp finish together).
+__device__ __forceinline__ float estimate_len(const double* tab, const float* ls, int N, int K, float lambda) {
+    const float l2lam = log2f(lambda);
+    const float l2s0 = log2f((float)tab[0]);
+    const float l2sN = log2f((float)tab[4 * (N - 1)]);
+    const float thr = -78.0f + fminf(0.0f, l2lam - l2s0);
+    const float d = l2sN - l2lam;                       // tail decay per state (> 0 when analysable)
+    const float L0 = (float)(N - 1) * l2lam - ls[N - 1];  // log2 p[N-1]
+    float est;
+    if (L0 >= thr || N == 1) {
+        est = (float)(N - 1) + (L0 - thr) / fmaxf(d, 1e-9f) + 2.0f;
+    } else {
+        // the chain dies inside the head: first j past the mode with log2 p[j] < thr
+        const unsigned hl = (unsigned)__double2hiint((double)lambda);
+        int lo = 1, hi = N - 1;  // smallest j with lambda < min(servRate[j..])
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (hl < (unsigned)__double2hiint(tab[4 * mid + 3])) hi = mid; else lo = mid + 1;
+        }
+        hi = N - 1;
+        while (lo < hi) {  // log2 p[j] = j*l2lam - ls[j] is decreasing past the mode
+            const int mid = (lo + hi) >> 1;
+            if ((float)mid * l2lam - ls[mid] < thr) hi = mid; else lo = mid + 1;
+        }
+        est = (float)lo + 2.0f;
+    }
+    return fminf(fmaxf(est, 2.0f), (float)K);
+}
+__device__ __forceinline__ int length_class(float est) {  // 0 = longest ... 254 = shortest
+    const int c = (int)(log2f(est) * 12.0f);  // ~6 % wide classes
+    return 254 - min(max(c, 0), 254);
+}
+
+__global__ void __launch_bounds__(256) grid_estimate(GridArgs g) {
+    __shared__ unsigned hist[kClasses];
+    const DevFleet& f = g.f;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * kSortChunk;
+    for (int k = threadIdx.x; k < kSortChunk; k += blockDim.x) {
+        const long long cell = base + k;
+        if (cell >= g.n_cells) break;
+        int s, a, bi, ri;
+        decode_cell(g, cell, s, a, bi, ri);
+        int key = 255;
+        const long long toff = g.pair_tab_off[s * f.A + a];
+        if (toff >= 0) {
+            const int b = g.batch[bi];
+            const int K = b + b * f.ratio;
+            const double* tab = g.tab + 4 * toff;
+            const float rmax = rate_max_of((float)tab[4 * (b - 1)]);
+            const float rate = __fdiv_rn(total_rate_of(f, s), (float)g.replicas[ri]);
+            if (!(rate <= 0.0f) && !(rate > rmax) && K >= 2) {  // Analyze: queueanalyzer.go:135-143
+                const float* ls = g.ls + toff + g.pair_tab_idx[s * f.A + a];
+                key = length_class(estimate_len(tab, ls, b, K, __fdiv_rn(rate, 1000.0f)));
+            }
+        }
+        g.keys[cell] = (uint8_t)key;
+        atomicAdd(&hist[key], 1u);
+    }
+    __syncthreads();
+    g.block_hist[(size_t)blockIdx.x * kClasses + threadIdx.x] = hist[threadIdx.x];
+}
+
+// one thread per class: running offsets over blocks, then class bases
+__global__ void __launch_bounds__(256) grid_scan(GridArgs g, int n_blocks) {
+    __shared__ unsigned total[kClasses];
+    const int c = threadIdx.x;
+    unsigned run = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        const unsigned v = g.block_hist[(size_t)b * kClasses + c];
+        g.block_hist[(size_t)b * kClasses + c] = run;
+        run += v;
+    }
+    total[c] = run;
+    __syncthreads();
+    if (c == 0) {
+        unsigned acc = 0;
+        for (int k = 0; k < kClasses; ++k) {
+            g.class_base[k] = acc;
+            acc += total[k];
+        }
+        g.class_base[kClasses] = acc - total[255];  // analysable cells
+    }
+}
+
+__global__ void __launch_bounds__(256) grid_scatter(GridArgs g) {
+    __shared__ unsigned cursor[kClasses];
+    cursor[threadIdx.x] = g.class_base[threadIdx.x] + g.block_hist[(size_t)blockIdx.x * kClasses + threadIdx.x];
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * kSortChunk;
+    for (int k = threadIdx.x; k < kSortChunk; k += blockDim.x) {
+        const long long cell = base + k;
+        if (cell >= g.n_cells) break;
+        const unsigned pos = atomicAdd(&cursor[g.keys[cell]], 1u);
+        g.order[pos] = (unsigned)cell;
+    }
+}
+
+// SLO feasibility of an analysed cell (the build's grid semantics)
+__device__ __forceinline__ bool cell_feasible(const DevFleet& f, int s, int r, float rate, float rmax, const Metrics& m) {
     const float slo_ttft = f.srv_slo_ttft[s], slo_itl = f.srv_slo_itl[s];
     bool feas = (slo_ttft == 0.0f || m.ttft <= slo_ttft) && (slo_itl == 0.0f || m.avg_token_time <= slo_itl) &&
                 (r >= f.srv_min_replicas[s]);
@@ -236,94 +375,54 @@ __device__ __forceinline__ void eval_grid_cell_tail(const DevFleet& f, int s, in
         const float lim = __fmul_rn(__fdiv_rn(rmax, 1000.0f), __fsub_rn(1.0f, 0.1f));
         feas = feas && (__fdiv_rn(rate, 1000.0f) <= lim);
     }
-    c = cand_nil();
-    if (feas) {
-        const long long total = (long long)num_instances(f, f.srv_model[s], a) * (long long)r;
-        c.feasible = 1;
-        c.acc = a;
-        c.replicas = r;
-        c.batch = b;
-        c.cost = __fmul_rn(f.acc_cost[a], (float)total);
-        c.value = penalty_of(f, s, c);
-        c.itl = m.avg_token_time;
-        c.ttft = m.ttft;
-        c.rho = m.rho;
-        c.max_rate = __fdiv_rn(rmax, 1000.0f);
-    }
+    return feas;
+}
+__device__ __forceinline__ void store_cell(const GridArgs& g, long long cell, int ok, int feas, const Metrics& m) {
+    g.cells.flags[cell] = (uint8_t)(ok | (feas << 1));
+    g.cells.ttft[cell] = m.ttft;
+    g.cells.itl[cell] = m.avg_token_time;
+    g.cells.rho[cell] = m.rho;
+    if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
 }
 
-// Work item = (batch chunk, replica level, server, accelerator): the 32 lanes of a warp take
-// 32 consecutive batch sizes of the descending-sorted batch list for ONE (server,
-// accelerator, replica) triple.  All lanes then share lambda and the service-rate table, and
-// their chains run in lock-step through the common head, so they end (early exit or K)
-// within a few steps of each other: no lane waits long for a slower neighbour.
 __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const DevFleet& f = g.f;
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(g.counter, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= g.n_items) break;
-        // item = ((chunk * R + ri) * S + s) * A + a  (largest batch sizes, then highest load first)
-        const int a = item % f.A;
-        unsigned t = item / f.A;
-        const int s = t % f.S;
-        t /= f.S;
-        const int ri = t % g.R;
-        const int chunk = t / g.R;
-        const int rank = chunk * 32 + lane;
-        const bool in_range = rank < g.B;
-        const int bi = g.batch_order[in_range ? rank : 0];
-        const int b = g.batch[bi];
-        const int r = g.replicas[ri];
-        const long long cell = (((long long)s * f.A + a) * g.B + bi) * g.R + ri;
-
-        Cand c = cand_nil();
-        Metrics m;
-        m.ttft = m.avg_token_time = m.rho = m.throughput = 0.0f;
-        int ok = 0;
-        const long long toff = g.pair_tab_off[s * f.A + a];
-        if (toff >= 0 && in_range) {  // pair passes the gates and carries load
-            const double* tab = g.tab + 4 * toff;
-            const int N = b, K = b + b * f.ratio;
-            Recip tail;
-            tail.b = tab[4 * (b - 1)];
-            tail.yh = tab[4 * (b - 1) + 1];
-            tail.yl = tab[4 * (b - 1) + 2];
-            const float rmax = rate_max_of((float)tail.b);
-            const float rate = __fdiv_rn(total_rate_of(f, s), (float)r);
-            // Analyze: queueanalyzer.go:135-150 (K >= 2 so the model is always valid)
-            if (!(rate <= 0.0f) && !(rate > rmax) && K >= 2) {
-                const float lambda = __fdiv_rn(rate, 1000.0f);
-                ModelStats st;
-                const int rc = solve_model<TAB_SHARED>(tab, 0, 0, N, K, lambda, tail, st);
-                if (rc == kSolveOk) {
-                    ok = 1;
-                    const QParams q = qparams_of(f, s, a);
-                    eval_grid_cell_tail(f, s, a, b, r, rate, rmax, q, st, c, m);
-                } else {
-                    const int k = atomicAdd(g.fb_count, 1);
-                    if (k < g.fb_cap) g.fb_cells[k] = cell;
-                }
-            }
-        }
-        if (in_range) {
-            if (g.cells.flags) g.cells.flags[cell] = (uint8_t)(ok | (c.feasible << 1));
-            if (g.cells.ttft) g.cells.ttft[cell] = m.ttft;
-            if (g.cells.itl) g.cells.itl[cell] = m.avg_token_time;
-            if (g.cells.rho) g.cells.rho[cell] = m.rho;
-            if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
-        }
-        c = cand_warp_min(c);
-        if (lane == 0) g.partials[(((size_t)s * f.A + a) * g.R + ri) * g.n_chunks + chunk] = c;
+    const unsigned n_active = g.class_base[kClasses];
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_active) return;
+    const long long cell = g.order[idx];
+    int s, a, bi, ri;
+    decode_cell(g, cell, s, a, bi, ri);
+    const int b = g.batch[bi], r = g.replicas[ri];
+    const double* tab = g.tab + 4 * g.pair_tab_off[s * f.A + a];
+    const int N = b, K = b + b * f.ratio;
+    Recip tail;
+    {
+        const double2 t0 = *(const double2*)(tab + 4 * (b - 1));
+        tail.b = t0.x;
+        tail.yh = t0.y;
+        tail.yl = tab[4 * (b - 1) + 2];
     }
+    const float rmax = rate_max_of((float)tail.b);
+    const float rate = __fdiv_rn(total_rate_of(f, s), (float)r);
+    const float lambda = __fdiv_rn(rate, 1000.0f);
+    ModelStats st;
+    const int rc = solve_model<TAB_SHARED>(tab, 0, 0, N, K, lambda, tail, st);
+    if (rc != kSolveOk) {
+        const int k = atomicAdd(g.fb_count, 1);
+        if (k < g.fb_cap) g.fb_cells[k] = cell;
+        return;
+    }
+    const QParams q = qparams_of(f, s, a);
+    const Metrics m = metrics_from(q, N, st);
+    const bool feas = cell_feasible(f, s, r, rate, rmax, m);
+    store_cell(g, cell, 1, feas ? 1 : 0, m);
+    if (feas) atomicMin(&g.best_rank[((size_t)s * f.A + a) * g.R + ri], g.batch_rank[bi]);
 }
 
 // Stored-vector re-run of bailed cells. One thread per slot; slot k handles cells
 // k, k + n_slots, ...  scratch per slot: (Kmax + 1) doubles then Nmax floats.
-__global__ void grid_fallback(GridArgs g, double* scratch, size_t slot_doubles, int Kmax, Cand* fb_cands,
-                              int* fb_status) {
+__global__ void grid_fallback(GridArgs g, double* scratch, size_t slot_doubles, int Kmax, int* fb_status) {
     const DevFleet& f = g.f;
     const int n_slots = gridDim.x * blockDim.x;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,50 +432,53 @@ __global__ void grid_fallback(GridArgs g, double* scratch, size_t slot_doubles, 
     float* sr = (float*)(p + Kmax + 1);  // servRate copy lives behind the p[0..Kmax] vector
     for (int k = slot; k < n; k += n_slots) {
         const long long cell = g.fb_cells[k];
-        const int ri = (int)(cell % g.R);
-        const int bi = (int)((cell / g.R) % g.B);
-        const int a = (int)((cell / ((long long)g.R * g.B)) % f.A);
-        const int s = (int)(cell / ((long long)g.R * g.B * f.A));
+        int s, a, bi, ri;
+        decode_cell(g, cell, s, a, bi, ri);
         const int b = g.batch[bi], r = g.replicas[ri];
         const double* tab = g.tab + 4 * g.pair_tab_off[s * f.A + a];
         for (int i = 0; i < b; ++i) sr[i] = (float)tab[4 * i];
         const float rmax = rate_max_of(sr[b - 1]);
         const float rate = __fdiv_rn(total_rate_of(f, s), (float)r);
-        const float lambda = __fdiv_rn(rate, 1000.0f);
         ModelStats st;
-        Cand c = cand_nil();
-        Metrics m;
-        m.ttft = m.avg_token_time = m.rho = m.throughput = 0.0f;
-        int ok = 0;
-        const int rc = solve_stored(p, sr, b, b + b * f.ratio, lambda, st);
-        if (rc == 0) {
-            ok = 1;
-            const QParams q = qparams_of(f, s, a);
-            eval_grid_cell_tail(f, s, a, b, r, rate, rmax, q, st, c, m);
-        } else {
+        const int rc = solve_stored(p, sr, b, b + b * f.ratio, __fdiv_rn(rate, 1000.0f), st);
+        if (rc != 0) {
             atomicExch(fb_status, rc);
+            continue;
         }
-        if (g.cells.flags) g.cells.flags[cell] = (uint8_t)(ok | (c.feasible << 1));
-        if (g.cells.ttft) g.cells.ttft[cell] = m.ttft;
-        if (g.cells.itl) g.cells.itl[cell] = m.avg_token_time;
-        if (g.cells.rho) g.cells.rho[cell] = m.rho;
-        if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
-        // the record's owner travels in `feasible` as server id + 1 (0 = infeasible)
-        c.feasible = c.feasible ? (s + 1) : 0;
-        fb_cands[k] = c;
+        const QParams q = qparams_of(f, s, a);
+        const Metrics m = metrics_from(q, b, st);
+        const bool feas = cell_feasible(f, s, r, rate, rmax, m);
+        store_cell(g, cell, 1, feas ? 1 : 0, m);
+        if (feas) atomicMin(&g.best_rank[((size_t)s * f.A + a) * g.R + ri], g.batch_rank[bi]);
     }
 }
 
-// K3: per-server argmin.  One CTA per server: strided scan of the server's partials,
-// warp-shuffle reduction, cross-warp reduction staged through shared memory.
-__global__ void __launch_bounds__(128) grid_finalize(GridArgs g, const Cand* fb_cands, AllocCols winners) {
+// K3: per-server argmin.  One CTA per server: one candidate per (accelerator, replica
+// level) = its smallest feasible batch size; warp-shuffle reduction, cross-warp reduction
+// staged through shared memory.
+__global__ void __launch_bounds__(128) grid_finalize(GridArgs g, AllocCols winners) {
     const DevFleet& f = g.f;
     const int s = blockIdx.x;
-    const int per_server = f.A * g.R * g.n_chunks;
-    const Cand* part = g.partials + (size_t)s * per_server;
     Cand best = cand_nil();
-    for (int i = threadIdx.x; i < per_server; i += blockDim.x) {
-        const Cand c = part[i];
+    for (int k = threadIdx.x; k < f.A * g.R; k += blockDim.x) {
+        const int a = k / g.R, ri = k % g.R;
+        const int rank = g.best_rank[((size_t)s * f.A + a) * g.R + ri];
+        if (rank == INT_MAX) continue;
+        const int bi = g.rank_to_bi[rank];
+        const int r = g.replicas[ri];
+        const long long cell = (((long long)s * f.A + a) * g.B + bi) * g.R + ri;
+        Cand c = cand_nil();
+        const long long total = (long long)num_instances(f, f.srv_model[s], a) * (long long)r;
+        c.feasible = 1;
+        c.acc = a;
+        c.replicas = r;
+        c.batch = g.batch[bi];
+        c.cost = __fmul_rn(f.acc_cost[a], (float)total);
+        c.value = penalty_of(f, s, c);
+        c.itl = g.cells.itl[cell];
+        c.ttft = g.cells.ttft[cell];
+        c.rho = g.cells.rho[cell];
+        c.max_rate = __fdiv_rn(rate_max_of((float)g.tab[4 * (g.pair_tab_off[s * f.A + a] + c.batch - 1)]), 1000.0f);
         if (cand_better(c, best)) best = c;
     }
     // zero-traffic servers: the reference's zeroLoadAllocation per candidate accelerator
@@ -384,16 +486,6 @@ __global__ void __launch_bounds__(128) grid_finalize(GridArgs g, const Cand* fb_
         if (pair_class(f, s, a, true) == PAIR_ZERO) {
             Cand c = zero_load_alloc(f, s, a);
             c.value = penalty_of(f, s, c);
-            if (cand_better(c, best)) best = c;
-        }
-    }
-    // stored-vector fallback records of this server
-    int nfb = *g.fb_count;
-    if (nfb > g.fb_cap) nfb = g.fb_cap;
-    for (int i = threadIdx.x; i < nfb; i += blockDim.x) {
-        Cand c = fb_cands[i];
-        if (c.feasible == s + 1) {
-            c.feasible = 1;
             if (cand_better(c, best)) best = c;
         }
     }
