@@ -139,7 +139,9 @@ struct wva_handle {
     int grid_Bmax = 0, grid_n_tab = 0;
     DevBuf d_grid_lists, d_pair_tab, d_tab_pair, d_tab_off, d_tab_len, d_tab, d_ls, d_sort, d_best;
     // shared
-    DevBuf d_cand_block, d_win_block, d_ctrl, d_fb_list, d_scratch, d_cells, d_sweep;
+    DevBuf d_cand_block, d_win_block, d_ctrl, d_fb_list, d_scratch, d_cells, d_sweep, d_dbg;
+    bool dbg_cycles = false;
+    size_t dbg_n = 0;
     PinBuf out_stage;
 
     int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -681,6 +683,12 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     g.fb_cap = (int)std::min<size_t>(nc, (size_t)1 << 22);
     CK(h->d_fb_list.ensure(sizeof(long long) * g.fb_cap));
     g.fb_cells = (long long*)h->d_fb_list.p;
+    if (h->dbg_cycles) {
+        CK(h->d_dbg.ensure(sizeof(unsigned) * nc * 2));
+        CK(cudaMemsetAsync(h->d_dbg.p, 0, sizeof(unsigned) * nc * 2, h->stream));
+        g.dbg_cycles = (unsigned*)h->d_dbg.p;
+        h->dbg_n = nc;
+    }
     plan->Bmax = Bmax;
     return WVA_OK;
 }
@@ -1058,6 +1066,22 @@ int wva_sweep(wva_handle* h, const wva_fleet* fleet, int32_t n_rates, wva_sweep_
     if (ctrl_host[CTRL_FB_COUNT] != 0)
         return h->fail(WVA_ERR_UNSUPPORTED, "sweep point outside the streaming solve's numeric window");
     return WVA_OK;
+}
+
+// ---- diagnostics (not part of the public ABI) ------------------------------------------
+// Per-cell SM cycles of the last grid solve, in launch order, followed by the cell ids.
+int wva_dbg_enable_cycles(wva_handle* h, int on) {
+    if (!h) return WVA_ERR_BAD_ARG;
+    h->dbg_cycles = on != 0;
+    return WVA_OK;
+}
+long long wva_dbg_read_cycles(wva_handle* h, unsigned* cycles, unsigned* cells, long long cap) {
+    if (!h || !h->d_dbg.p) return 0;
+    const long long n = std::min<long long>((long long)h->dbg_n, cap);
+    cudaMemcpy(cycles, h->d_dbg.p, sizeof(unsigned) * n, cudaMemcpyDeviceToHost);
+    char* w = (char*)h->d_sort.p;
+    cudaMemcpy(cells, w + align_up(std::max<size_t>(h->dbg_n, 1)), sizeof(unsigned) * n, cudaMemcpyDeviceToHost);
+    return n;
 }
 
 }  // extern "C"

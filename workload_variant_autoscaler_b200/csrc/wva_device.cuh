@@ -194,15 +194,19 @@ __device__ __forceinline__ double step_fast(const void* tab, int stride, int n, 
 template <int TAB>
 __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono, int N, int K, float lambda,
                                         const Recip& tail, ModelStats& st) {
+    // Lanes enter together and leave together: no early return, explicit re-convergence
+    // after each variable-trip-count loop (otherwise lanes that finish pass 1 early run
+    // pass 2 on their own and the warp serialises).
+    const unsigned warp_mask = __activemask();
     const double lam = (double)lambda;
-    if (!in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail.b, kHiRateLo, kHiRateHi)) return kSolveBail;
+    bool bail = !in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail.b, kHiRateLo, kHiRateHi);
     const int nh = N - 1;  // steps n < nh read servRate[n] from the table; the rest use the tail
     // in the tail p is non-increasing iff lambda < servRate[N-1] (with a margin for rounding)
     const bool tail_mono = (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tail.b);
 
     // ---- p[1] and the negligibility threshold --------------------------------------
-    double p = step_fast<TAB>(tab, stride, 0, nh, tail, lam);  // RN(1*lambda) = lambda
-    if (!(p >= 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
+    double p = bail ? 0.0 : step_fast<TAB>(tab, stride, 0, nh, tail, lam);  // RN(1*lambda) = lambda
+    if (!(p >= 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) bail = true;
     const double p1 = p;
     unsigned thr_hi = 0;  // early exit when hi(p) < thr_hi; 0 disables it
     if (K < (1 << 23)) thr_hi = (unsigned)__double2hiint(__dmul_rn(fmin(1.0, p1), 0x1p-78));
@@ -210,13 +214,14 @@ __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono,
     // ---- pass 1: normalising sum ------------------------------------------------
     double sum = __dadd_rn(1.0, p);
     int j_end = K + 1;  // first state index that is skipped (K + 1: nothing skipped)
+    const int n_stop = bail ? 0 : K;
 #pragma unroll 2
-    for (int n = 1; n < K; ++n) {  // p holds p[n]
+    for (int n = 1; n < n_stop; ++n) {  // p holds p[n]
         if (in_window(p, kHiPLo, kHiPHi)) {
             p = step_fast<TAB>(tab, stride, n, nh, tail, __dmul_rn(p, lam));
         } else {
             if (p == 0.0) { j_end = n + 1; break; }
-            if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return kSolveBail;
+            if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) { bail = true; break; }
             p = __ddiv_rn(__dmul_rn(p, lam), step_recip<TAB>(tab, stride, n, nh, tail).b);
         }
         sum = __dadd_rn(sum, p);
@@ -228,7 +233,9 @@ __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono,
             }
         }
     }
-    if (!in_window(sum, kHiSumLo, kHiSumHi)) return kSolveBail;
+    __syncwarp(warp_mask);
+    if (!in_window(sum, kHiSumLo, kHiSumHi)) bail = true;
+    if (bail) { sum = 1.0; j_end = 1; }
 
     // ---- pass 2: normalise, accumulate states 1 .. j_end-1 ----------------------------
     // (pass 1 established that states >= j_end contribute nothing)
@@ -237,6 +244,7 @@ __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono,
     double acc = 0.0, sum_p = pn0, pn = 0.0, di = 1.0, acc_at_N = 0.0;
     bool captured = false;
     p = p1;
+    __syncwarp(warp_mask);
 #pragma unroll 2
     for (int i = 1; i < j_end; ++i) {
         const bool fast = in_window(p, kHiPLo, kHiPHi);
@@ -260,6 +268,7 @@ __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono,
                 p = __ddiv_rn(a, step_recip<TAB>(tab, stride, i, nh, tail).b);
         }
     }
+    __syncwarp(warp_mask);
     // when the chain ended before state N the remaining updates of acc and sumP are no-ops
     if (!captured) acc_at_N = acc;
     const double in_serv = __dadd_rn(acc_at_N, __dmul_rn(__dsub_rn(1.0, sum_p), (double)N));
@@ -275,7 +284,7 @@ __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono,
     float w = __fsub_rn(st.avg_resp_time, st.avg_serv_time);
     if (w < 0.0f) w = 0.0f;
     st.avg_wait_time = w;
-    return kSolveOk;
+    return bail ? kSolveBail : kSolveOk;
 }
 
 // Stored-vector fallback: a literal restatement of computeProbabilities /

@@ -255,6 +255,7 @@ struct GridArgs {
     int* fb_count;           // cells that need the stored-vector fallback
     long long* fb_cells;
     int fb_cap;
+    unsigned* dbg_cycles;    // diagnostics: per order index, SM cycles spent in grid_kernel (or NULL)
 };
 
 __device__ __forceinline__ void decode_cell(const GridArgs& g, long long cell, int& s, int& a, int& bi, int& ri) {
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const unsigned n_active = g.class_base[kClasses];
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_active) return;
+    const long long t_start = g.dbg_cycles ? clock64() : 0;
     const long long cell = g.order[idx];
     int s, a, bi, ri;
     decode_cell(g, cell, s, a, bi, ri);
@@ -418,6 +420,7 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const bool feas = cell_feasible(f, s, r, rate, rmax, m);
     store_cell(g, cell, 1, feas ? 1 : 0, m);
     if (feas) atomicMin(&g.best_rank[((size_t)s * f.A + a) * g.R + ri], g.batch_rank[bi]);
+    if (g.dbg_cycles) g.dbg_cycles[idx] = (unsigned)(clock64() - t_start);
 }
 
 // Stored-vector re-run of bailed cells. One thread per slot; slot k handles cells
