@@ -193,11 +193,12 @@ __device__ __forceinline__ double step_fast(const void* tab, int stride, int n, 
 // sizes stay converged: only the trip count differs between lanes.
 template <int TAB>
 __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono, int N, int K, float lambda,
-                                        const Recip& tail, ModelStats& st) {
+                                        const Recip& tail_in, ModelStats& st) {
     // Lanes enter together and leave together: no early return, explicit re-convergence
     // after each variable-trip-count loop (otherwise lanes that finish pass 1 early run
     // pass 2 on their own and the warp serialises).
     const unsigned warp_mask = __activemask();
+    const Recip tail = tail_in;  // keep the tail triple in registers (the reference lives in local memory)
     const double lam = (double)lambda;
     bool bail = !in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail.b, kHiRateLo, kHiRateHi);
     const int nh = N - 1;  // steps n < nh read servRate[n] from the table; the rest use the tail
@@ -276,6 +277,129 @@ __device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono,
     const double pnK = (j_end == K + 1) ? pn : 0.0;
 
     // ---- float32 tail: mm1modelstatedependent.go:56-66 --------------------------
+    st.avg_num_in_servers = (float)in_serv;
+    const float avg_num_in_system = (float)acc;
+    st.throughput = __fmul_rn(lambda, __fsub_rn(1.0f, (float)pnK));
+    st.avg_resp_time = __fdiv_rn(avg_num_in_system, st.throughput);
+    st.avg_serv_time = __fdiv_rn(st.avg_num_in_servers, st.throughput);
+    float w = __fsub_rn(st.avg_resp_time, st.avg_serv_time);
+    if (w < 0.0f) w = 0.0f;
+    st.avg_wait_time = w;
+    return bail ? kSolveBail : kSolveOk;
+}
+
+// ---------------------------------------------------------------------------
+// Shared-table solver (grid and sweep kernels): same arithmetic as solve_model<TAB_SHARED>,
+// restructured for issue efficiency.  The hot loops contain only the recurrence: one merged
+// exponent-window test per step covers "p is negligible / zero / tiny / too large"; the
+// reciprocal triple stays in registers and is re-loaded only while n <= N-1 (table entry
+// N-1 is the tail, so no select between head and tail values is needed); everything rare
+// (exit test, exact division for tiny p, bail-out) lives in an outer handler.
+// tab: 4 doubles per entry {servRate[n], yh, yl, suffix-min}, at least N entries.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_recip(const double* __restrict__ tab, int n, Recip& r) {
+    const double2 t0 = *(const double2*)(tab + 4 * n);
+    r.b = t0.x;
+    r.yh = t0.y;
+    r.yl = tab[4 * n + 2];
+}
+
+__device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st) {
+    const unsigned warp_mask = __activemask();
+    const double lam = (double)lambda;
+    const int nh = N - 1;
+    Recip cur;
+    load_recip(tab, 0, cur);
+    const double tail_b = tab[4 * nh];
+    bool bail = !in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail_b, kHiRateLo, kHiRateHi) ||
+                !in_window(cur.b, kHiRateLo, kHiRateHi);
+    const bool tail_mono = (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tail_b);
+
+    double p = bail ? 0.0 : div_recip(lam, cur);  // p[1]; RN(1*lambda) = lambda
+    if (!(p >= 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) bail = true;
+    const double p1 = p;
+    unsigned thr_hi = 0;
+    if (K < (1 << 23)) thr_hi = (unsigned)__double2hiint(__dmul_rn(fmin(1.0, p1), 0x1p-78));
+    // merged fast window [max(thr, 2^-280), 2^600): inside it the step is a plain reciprocal step
+    const unsigned lo_eff = thr_hi > kHiPLo ? thr_hi : kHiPLo;
+    const unsigned span_eff = kHiPHi - lo_eff;
+
+    // ---- pass 1 -----------------------------------------------------------------
+    double sum = __dadd_rn(1.0, p);
+    int j_end = K + 1;
+    {
+        int n = 1;  // p holds p[n]
+        const int n_stop = bail ? 0 : K;
+        while (n < n_stop) {
+#pragma unroll 2
+            while (n < n_stop && ((unsigned)__double2hiint(p) - lo_eff) < span_eff) {
+                if (n <= nh) load_recip(tab, n, cur);
+                p = div_recip(__dmul_rn(p, lam), cur);
+                sum = __dadd_rn(sum, p);
+                ++n;
+            }
+            if (n >= n_stop) break;
+            // p[n] is outside the fast window
+            const unsigned hp = (unsigned)__double2hiint(p);
+            if (hp < thr_hi && (n >= nh ? tail_mono : (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tab[4 * n + 3]))) {
+                j_end = n + 1;  // negligible and past the mode: states > n contribute nothing
+                break;
+            }
+            if (p == 0.0) { j_end = n + 1; break; }
+            if (!(p > 0.0) || hp >= kHiPHi) { bail = true; break; }
+            // rare: exact IEEE division for one step
+            if (n <= nh) load_recip(tab, n, cur);
+            p = hp >= kHiPLo ? div_recip(__dmul_rn(p, lam), cur) : __ddiv_rn(__dmul_rn(p, lam), cur.b);
+            sum = __dadd_rn(sum, p);
+            ++n;
+        }
+    }
+    __syncwarp(warp_mask);
+    if (!in_window(sum, kHiSumLo, kHiSumHi)) bail = true;
+    if (bail) { sum = 1.0; j_end = 1; }
+
+    // ---- pass 2 -----------------------------------------------------------------
+    const Recip z = make_recip(sum);
+    double acc = 0.0, sum_p = z.yh, pn = 0.0, di = 1.0, acc_at_N = 0.0;
+    p = p1;
+    load_recip(tab, nh > 0 ? 1 : 0, cur);  // rate of the step out of state 1
+    __syncwarp(warp_mask);
+    {
+        int i = 1;  // p holds p[i]
+        while (i < j_end) {
+#pragma unroll 2
+            while (i < j_end && ((unsigned)__double2hiint(p) - kHiPLo) < (kHiPHi - kHiPLo)) {
+                pn = div_recip(p, z);
+                acc = __dadd_rn(acc, __dmul_rn(di, pn));
+                di = __dadd_rn(di, 1.0);
+                if (i <= N) {
+                    sum_p = __dadd_rn(sum_p, pn);
+                    acc_at_N = acc;
+                }
+                if (i <= nh) load_recip(tab, i, cur);
+                p = div_recip(__dmul_rn(p, lam), cur);  // p[i+1] (unused after the last state)
+                ++i;
+            }
+            if (i >= j_end) break;
+            if (p == 0.0) { pn = 0.0; break; }
+            // rare: tiny p, exact IEEE divisions
+            pn = __ddiv_rn(p, sum);
+            acc = __dadd_rn(acc, __dmul_rn(di, pn));
+            di = __dadd_rn(di, 1.0);
+            if (i <= N) {
+                sum_p = __dadd_rn(sum_p, pn);
+                acc_at_N = acc;
+            }
+            if (i <= nh) load_recip(tab, i, cur);
+            p = __ddiv_rn(__dmul_rn(p, lam), cur.b);
+            ++i;
+        }
+    }
+    __syncwarp(warp_mask);
+    // acc_at_N tracked acc while i <= N: it holds acc at state min(N, last state)
+    const double in_serv = __dadd_rn(acc_at_N, __dmul_rn(__dsub_rn(1.0, sum_p), (double)N));
+    const double pnK = (j_end == K + 1) ? pn : 0.0;
+
     st.avg_num_in_servers = (float)in_serv;
     const float avg_num_in_system = (float)acc;
     st.throughput = __fmul_rn(lambda, __fsub_rn(1.0f, (float)pnK));

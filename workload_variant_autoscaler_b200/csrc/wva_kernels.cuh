@@ -398,18 +398,11 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const int b = g.batch[bi], r = g.replicas[ri];
     const double* tab = g.tab + 4 * g.pair_tab_off[s * f.A + a];
     const int N = b, K = b + b * f.ratio;
-    Recip tail;
-    {
-        const double2 t0 = *(const double2*)(tab + 4 * (b - 1));
-        tail.b = t0.x;
-        tail.yh = t0.y;
-        tail.yl = tab[4 * (b - 1) + 2];
-    }
-    const float rmax = rate_max_of((float)tail.b);
+    const float rmax = rate_max_of((float)tab[4 * (b - 1)]);
     const float rate = __fdiv_rn(total_rate_of(f, s), (float)r);
     const float lambda = __fdiv_rn(rate, 1000.0f);
     ModelStats st;
-    const int rc = solve_model<TAB_SHARED>(tab, 0, 0, N, K, lambda, tail, st);
+    const int rc = solve_shared(tab, N, K, lambda, st);
     if (rc != kSolveOk) {
         const int k = atomicAdd(g.fb_count, 1);
         if (k < g.fb_cap) g.fb_cells[k] = cell;
@@ -803,7 +796,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepArgs g) {
         if (!(rate <= 0.0f) && !(rate > rmax) && K >= 2) {
             ModelStats st;
             const QParams q = qparams_of(f, s, a);
-            if (solve_model<TAB_SHARED>(tab, 0, 0, N, K, __fdiv_rn(rate, 1000.0f), tail, st) == kSolveOk) {
+            if (solve_shared(tab, N, K, __fdiv_rn(rate, 1000.0f), st) == kSolveOk) {
                 m = metrics_from(q, N, st);
                 ok = 1;
             } else {
