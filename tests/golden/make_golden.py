@@ -1,0 +1,92 @@
+"""Generate the committed golden fixtures (run from the repo root: python tests/golden/make_golden.py).
+
+The reference is Go and cannot be run in this image, so these vectors are NOT outputs of the
+Go binary: they are outputs of the C oracle (oracle/wva_oracle.c) on inputs built from the
+reference's own fixtures, frozen so that oracle or kernel regressions are caught, and
+cross-checked at generation time against the independent numpy restatement.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import oracle  # noqa: E402
+from oracle import restate_np as R  # noqa: E402
+from workload_variant_autoscaler_b200 import Fleet, Grid, synth_fleet  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def config1_fleet(arrival_rpm, in_tok, out_tok):
+    """BASELINE configs[0]: the single VariantAutoscaling of deploy/examples/vllm-emulator
+    (vllme-variantautoscaling.yaml:26-37: A100 alpha 20.58 beta 0.41 gamma 5.2 delta 0.1, maxBatch 4;
+    deploy/configmap-*.yaml: A100 cost 40.00, Premium slo-tpot 24 / slo-ttft 500), production flags
+    (unlimited, keepAccelerator, minReplicas 1: internal/utils/utils.go:170-173,290)."""
+    spec = {
+        "acceleratorData": {"accelerators": [{"name": "A100", "type": "NVIDIA-A100-PCIE-80GB", "multiplicity": 1,
+                                              "cost": 40.0}]},
+        "modelData": {"models": [{"name": "default/default", "acc": "A100", "accCount": 1, "maxBatchSize": 4,
+                                  "decodeParms": {"alpha": 20.58, "beta": 0.41},
+                                  "prefillParms": {"gamma": 5.2, "delta": 0.1}}]},
+        "serviceClassData": {"serviceClasses": [{"name": "Premium", "priority": 1, "modelTargets": [
+            {"model": "default/default", "slo-itl": 24.0, "slo-ttft": 500.0}]}]},
+        "serverData": {"servers": [{"name": "vllme-deployment:llm-d-sim", "model": "default/default",
+                                    "class": "Premium", "keepAccelerator": True, "minNumReplicas": 1,
+                                    "maxBatchSize": 4,
+                                    "currentAlloc": {"accelerator": "A100", "numReplicas": 1, "cost": 40.0,
+                                                     "load": {"arrivalRate": arrival_rpm, "avgInTokens": in_tok,
+                                                              "avgOutTokens": out_tok}}}]},
+        "optimizerData": {"optimizer": {"unlimited": True}},
+    }
+    return Fleet.from_spec(spec)
+
+
+CONFIG1_LOADS = (0.0, 60.0, 480.0, 960.0, 1440.0)
+CONFIG1_TOKENS = ((0, 278), (128, 128))  # emulator through the collector; and the 128/128 variant
+
+
+def main():
+    out = {}
+    # --- config 1 -------------------------------------------------------------------------
+    rows = []
+    for it, ot in CONFIG1_TOKENS:
+        for rpm in CONFIG1_LOADS:
+            f = config1_fleet(rpm, it, ot)
+            cand, win = oracle.solve(f)
+            r = R.create_allocation(f, 0, 0)
+            w = win[0]
+            assert int(w["feasible"]) == r["feasible"]
+            if r["feasible"]:
+                assert int(w["replicas"]) == r["replicas"]
+                for k in ("cost", "itl", "ttft", "rho", "max_rate"):
+                    assert np.float32(w[k]).view(np.uint32) == np.float32(r[k]).view(np.uint32), (rpm, k)
+            rows.append(w)
+    out["config1_winners"] = np.array(rows, dtype=oracle.ALLOC_DTYPE)
+    # --- small synthetic fleet: size candidates, winners, grid, sweep -------------------------
+    f = synth_fleet(12, 3, seed=2024, max_batch_choices=(2, 4, 8, 16, 32), zero_load_frac=0.15)
+    f.srv_min_replicas[::5] = 0
+    cand, win = oracle.solve(f)
+    for s in range(f.n_servers):  # cross-check a subset against the numpy restatement
+        for a in range(0, f.n_acc, 2):
+            r = R.create_allocation(f, s, a)
+            o = oracle.create_allocation(f, s, a)
+            assert o["feasible"] == r["feasible"]
+            if r["feasible"]:
+                assert o["replicas"] == r["replicas"]
+                assert np.float32(o["ttft"]).view(np.uint32) == np.float32(r["ttft"]).view(np.uint32)
+    out["synth_cand"], out["synth_win"] = cand, win
+    grid = Grid([1, 2, 4, 8, 16, 31], [1, 2, 3, 4, 6, 8, 12, 16, 24, 33])
+    cells, gwin = oracle.grid_solve(f, grid)
+    out["grid_cells"], out["grid_win"] = cells, gwin
+    sw = oracle.sweep(f, 16)
+    for k, v in sw.items():
+        out["sweep_" + k] = v
+    np.savez_compressed(os.path.join(HERE, "golden_r01.npz"), **out)
+    print("wrote golden_r01.npz:", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

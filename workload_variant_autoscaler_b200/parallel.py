@@ -1,0 +1,68 @@
+"""Multi-GPU driver: one process per GPU, servers sharded round-robin, ONE all-gather.
+
+Unlimited mode is separable per server (pkg/solver/solver.go:63-79): every rank analyses and
+solves its own servers with no data-path exchange, then the fixed-size winner records
+(10 x 4 B per server) are all-gathered (NCCL over NVLink on GPUs; gloo in the CPU tests) and
+every rank ends up with the full ``AllocationSolution``.  The accelerator / model tables are
+tiny and simply replicated.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._abi import ALLOC_COLUMNS, Allocs
+from .fleet import Fleet
+
+
+def shard_indices(n_servers: int, rank: int, world: int) -> np.ndarray:
+    return np.arange(n_servers)[rank::world]
+
+
+def pack_winners(win: Allocs, pad_to: int) -> np.ndarray:
+    """Allocs -> int32 [10, pad_to] (float columns bit-cast), padding = infeasible records."""
+    out = np.zeros((len(ALLOC_COLUMNS), pad_to), np.int32)
+    for k, (name, dt) in enumerate(ALLOC_COLUMNS):
+        col = getattr(win, name)
+        out[k, : win.n] = col.astype(np.int32) if dt is np.uint8 else col.view(np.int32)
+    return out
+
+
+def unpack_winners(blocks: np.ndarray, n_servers: int, world: int) -> Allocs:
+    """int32 [world, 10, pad] gathered blocks -> Allocs in the original server order."""
+    out = Allocs(n_servers)
+    for r in range(world):
+        idx = shard_indices(n_servers, r, world)
+        for k, (name, dt) in enumerate(ALLOC_COLUMNS):
+            col = blocks[r, k, : idx.size]
+            getattr(out, name)[idx] = col.astype(np.uint8) if dt is np.uint8 else col.view(dt)
+    return out
+
+
+def solve_sharded(solve_local, fleet: Fleet, *, rank: int, world: int, all_gather) -> Allocs:
+    """Solve ``fleet`` across ``world`` ranks.
+
+    solve_local(shard: Fleet) -> Allocs of the shard's winners (the engine on this rank's GPU);
+    all_gather(block: np.ndarray[int32]) -> np.ndarray [world, ...] (one collective).
+    """
+    shard = fleet.shard(rank, world)
+    win = solve_local(shard)
+    pad = (fleet.n_servers + world - 1) // world
+    gathered = all_gather(pack_winners(win, pad))
+    return unpack_winners(np.asarray(gathered), fleet.n_servers, world)
+
+
+def torch_all_gather(group=None, device=None):
+    """all_gather callable over torch.distributed (nccl on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+
+    def _ag(block: np.ndarray) -> np.ndarray:
+        world = dist.get_world_size(group)
+        t = torch.from_numpy(np.ascontiguousarray(block)).reshape(-1)
+        if device is not None:
+            t = t.to(device)
+        out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out.cpu().numpy().reshape((world,) + tuple(block.shape))
+
+    return _ag
