@@ -137,7 +137,7 @@ struct wva_handle {
     uint64_t grid_epoch = ~0ull;
     std::vector<int> grid_batch, grid_replicas;
     int grid_Bmax = 0, grid_n_tab = 0;
-    DevBuf d_grid_lists, d_pair_tab, d_tab_pair, d_tab_off, d_tab_len, d_tab, d_ls, d_sort, d_best;
+    DevBuf d_grid_lists, d_pair_tab, d_tab_pair, d_tab_off, d_tab_len, d_tab, d_ls, d_sort, d_best, d_pb;
     // shared
     DevBuf d_cand_block, d_win_block, d_ctrl, d_fb_list, d_scratch, d_cells, d_sweep, d_dbg;
     bool dbg_cycles = false;
@@ -640,11 +640,17 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     // the tables are rebuilt on every call (only the host-side work lists are cached):
     // they are part of the evaluation, not an input
     if (h->grid_n_tab) {
+        CK(h->d_pb.ensure(sizeof(float4) * ((size_t)h->grid_n_tab * std::max(B, 1) + (size_t)S * std::max(R, 1) + 1)));
+        float4* d_pb = (float4*)h->d_pb.p;
+        float4* d_rt = d_pb + (size_t)h->grid_n_tab * std::max(B, 1);
         build_pair_tables<<<h->grid_n_tab, 128, 0, h->stream>>>(h->df, (const int*)h->d_tab_pair.p,
                                                                 (const long long*)h->d_tab_off.p,
                                                                 (const int*)h->d_tab_len.p, h->grid_n_tab,
-                                                                (double*)h->d_tab.p, (float*)h->d_ls.p);
-        h->launches++;
+                                                                (double*)h->d_tab.p, (float*)h->d_ls.p,
+                                                                (const int*)h->d_grid_lists.p, B, d_pb);
+        if (S * R > 0)
+            grid_rates<<<(S * R + 255) / 256, 256, 0, h->stream>>>(h->df, (const int*)h->d_grid_lists.p + 3 * B, R, d_rt);
+        h->launches += 2;
         CK(cudaGetLastError());
     }
     GridArgs& g = plan->args;
@@ -660,6 +666,8 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     g.ls = (const float*)h->d_ls.p;
     g.pair_tab_off = d_pair_off;
     g.pair_tab_idx = d_pair_idx;
+    g.pb = (const float4*)h->d_pb.p;
+    g.rt = g.pb + (size_t)h->grid_n_tab * std::max(B, 1);
     const unsigned long long n_cells = (unsigned long long)S * A * B * R;
     if (n_cells > 0xfffffff0ull) return h->fail(WVA_ERR_UNSUPPORTED, "grid too large for one call (>= 2^32 cells)");
     g.n_cells = (long long)n_cells;
@@ -782,7 +790,7 @@ void wva_destroy(wva_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->arena, &h->d_cand_pair, &h->d_cand_N, &h->d_group_off, &h->d_ltab, &h->d_grid_lists,
-                      &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_ls, &h->d_sort, &h->d_best,
+                      &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_ls, &h->d_sort, &h->d_best, &h->d_pb,
                       &h->d_cand_block, &h->d_win_block, &h->d_ctrl, &h->d_fb_list, &h->d_scratch,
                       &h->d_cells, &h->d_sweep};
     for (DevBuf* b : bufs) b->release();
@@ -1017,7 +1025,8 @@ int wva_sweep(wva_handle* h, const wva_fleet* fleet, int32_t n_rates, wva_sweep_
         CK(cudaMemcpyAsync(h->d_tab_len.p, lens.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
         h->grid_epoch = ~0ull;  // the shared-table buffers now hold sweep tables
         build_pair_tables<<<n, 128, 0, h->stream>>>(h->df, (const int*)h->d_tab_pair.p, (const long long*)h->d_tab_off.p,
-                                                    (const int*)h->d_tab_len.p, n, (double*)h->d_tab.p, nullptr);
+                                                    (const int*)h->d_tab_len.p, n, (double*)h->d_tab.p, nullptr,
+                                                    nullptr, 0, nullptr);
         h->launches++;
         SweepArgs g{};
         g.f = h->df;

@@ -304,18 +304,23 @@ __device__ __forceinline__ void load_recip(const double* __restrict__ tab, int n
     r.yl = tab[4 * n + 2];
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Fast-window test on the high word: lo <= hi(p) < lo + span.
+#define WVA_FASTWIN(p, lo, span) ((((unsigned)__double2hiint(p)) - (lo)) < (span))
+
 __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st) {
     const unsigned warp_mask = __activemask();
     const double lam = (double)lambda;
     const int nh = N - 1;
-    Recip cur;
-    load_recip(tab, 0, cur);
+    Recip A, B;  // reciprocal triples of two consecutive steps (software-pipelined table loads)
+    load_recip(tab, 0, A);
     const double tail_b = tab[4 * nh];
     bool bail = !in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail_b, kHiRateLo, kHiRateHi) ||
-                !in_window(cur.b, kHiRateLo, kHiRateHi);
+                !in_window(A.b, kHiRateLo, kHiRateHi);
     const bool tail_mono = (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tail_b);
 
-    double p = bail ? 0.0 : div_recip(lam, cur);  // p[1]; RN(1*lambda) = lambda
+    double p = bail ? 0.0 : div_recip(lam, A);  // p[1]; RN(1*lambda) = lambda
     if (!(p >= 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) bail = true;
     const double p1 = p;
     unsigned thr_hi = 0;
@@ -331,10 +336,21 @@ __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, 
         int n = 1;  // p holds p[n]
         const int n_stop = bail ? 0 : K;
         while (n < n_stop) {
-#pragma unroll 2
-            while (n < n_stop && ((unsigned)__double2hiint(p) - lo_eff) < span_eff) {
-                if (n <= nh) load_recip(tab, n, cur);
-                p = div_recip(__dmul_rn(p, lam), cur);
+            // (re-)establish: A = triple of step n, B = triple of step n+1
+            load_recip(tab, n < nh ? n : nh, A);
+            load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
+            for (;;) {
+                if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) break;
+                if (n < nh) {  // triple of step n+2 (B already holds n+1); prefetch two lines ahead
+                    prefetch_l1(tab + 4 * (n + 10));
+                }
+                p = div_recip(__dmul_rn(p, lam), A);
+                if (n < nh) load_recip(tab, n + 2 < nh ? n + 2 : nh, A);
+                sum = __dadd_rn(sum, p);
+                ++n;
+                if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) break;
+                p = div_recip(__dmul_rn(p, lam), B);
+                if (n < nh) load_recip(tab, n + 2 < nh ? n + 2 : nh, B);
                 sum = __dadd_rn(sum, p);
                 ++n;
             }
@@ -347,9 +363,9 @@ __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, 
             }
             if (p == 0.0) { j_end = n + 1; break; }
             if (!(p > 0.0) || hp >= kHiPHi) { bail = true; break; }
-            // rare: exact IEEE division for one step
-            if (n <= nh) load_recip(tab, n, cur);
-            p = hp >= kHiPLo ? div_recip(__dmul_rn(p, lam), cur) : __ddiv_rn(__dmul_rn(p, lam), cur.b);
+            // rare: one step outside the fast loop (exact IEEE division when p is tiny)
+            load_recip(tab, n < nh ? n : nh, A);
+            p = hp >= kHiPLo ? div_recip(__dmul_rn(p, lam), A) : __ddiv_rn(__dmul_rn(p, lam), A.b);
             sum = __dadd_rn(sum, p);
             ++n;
         }
@@ -362,27 +378,43 @@ __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, 
     const Recip z = make_recip(sum);
     double acc = 0.0, sum_p = z.yh, pn = 0.0, di = 1.0, acc_at_N = 0.0;
     p = p1;
-    load_recip(tab, nh > 0 ? 1 : 0, cur);  // rate of the step out of state 1
     __syncwarp(warp_mask);
     {
         int i = 1;  // p holds p[i]
         while (i < j_end) {
-#pragma unroll 2
-            while (i < j_end && ((unsigned)__double2hiint(p) - kHiPLo) < (kHiPHi - kHiPLo)) {
+            load_recip(tab, i < nh ? i : nh, A);  // triple of the step out of state i
+            load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
+            for (;;) {
+                if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
+                if (i < nh) prefetch_l1(tab + 4 * (i + 10));
                 pn = div_recip(p, z);
+                const double a0 = __dmul_rn(p, lam);
                 acc = __dadd_rn(acc, __dmul_rn(di, pn));
                 di = __dadd_rn(di, 1.0);
                 if (i <= N) {
                     sum_p = __dadd_rn(sum_p, pn);
                     acc_at_N = acc;
                 }
-                if (i <= nh) load_recip(tab, i, cur);
-                p = div_recip(__dmul_rn(p, lam), cur);  // p[i+1] (unused after the last state)
+                p = div_recip(a0, A);  // p[i+1] (unused after the last state)
+                if (i < nh) load_recip(tab, i + 2 < nh ? i + 2 : nh, A);
+                ++i;
+                if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
+                pn = div_recip(p, z);
+                const double a1 = __dmul_rn(p, lam);
+                acc = __dadd_rn(acc, __dmul_rn(di, pn));
+                di = __dadd_rn(di, 1.0);
+                if (i <= N) {
+                    sum_p = __dadd_rn(sum_p, pn);
+                    acc_at_N = acc;
+                }
+                p = div_recip(a1, B);
+                if (i < nh) load_recip(tab, i + 2 < nh ? i + 2 : nh, B);
                 ++i;
             }
             if (i >= j_end) break;
             if (p == 0.0) { pn = 0.0; break; }
             // rare: tiny p, exact IEEE divisions
+            load_recip(tab, i < nh ? i : nh, A);
             pn = __ddiv_rn(p, sum);
             acc = __dadd_rn(acc, __dmul_rn(di, pn));
             di = __dadd_rn(di, 1.0);
@@ -390,8 +422,7 @@ __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, 
                 sum_p = __dadd_rn(sum_p, pn);
                 acc_at_N = acc;
             }
-            if (i <= nh) load_recip(tab, i, cur);
-            p = __ddiv_rn(__dmul_rn(p, lam), cur.b);
+            p = __ddiv_rn(__dmul_rn(p, lam), A.b);
             ++i;
         }
     }

@@ -174,9 +174,17 @@ __device__ __forceinline__ Cand zero_load_alloc(const DevFleet& f, int s, int a)
 // as doubles (32 B, two 16 B loads per head step), plus a float column
 // ls[n] = sum_{i<n} log2(servRate[i]) used only to ESTIMATE chain lengths for scheduling.
 // ---------------------------------------------------------------------------
-__global__ void build_pair_tables(DevFleet f, const int* __restrict__ tab_pair, const long long* __restrict__ tab_off,
-                                  const int* __restrict__ tab_len, int n_tab, double* __restrict__ tab,
-                                  float* __restrict__ ls) {
+// Per (table, batch index) constants shared by the 64 replica levels of a pair:
+// x = RateRange.Max (req/s) for N = batch, y = log2 servRate[N-1], z = ls[N-1], w = log2 servRate[0].
+// Per (server, replica index): x = rate (req/s), y = lambda (req/ms), z = log2 lambda.
+__global__ void __launch_bounds__(128) build_pair_tables(DevFleet f, const int* __restrict__ tab_pair,
+                                                         const long long* __restrict__ tab_off,
+                                                         const int* __restrict__ tab_len, int n_tab,
+                                                         double* __restrict__ tab, float* __restrict__ ls,
+                                                         const int* __restrict__ batch, int B,
+                                                         float4* __restrict__ pb) {
+    __shared__ double wsum[4];
+    __shared__ double carry_s;
     const int t = blockIdx.x;
     if (t >= n_tab) return;
     const int pair = tab_pair[t];
@@ -184,30 +192,81 @@ __global__ void build_pair_tables(DevFleet f, const int* __restrict__ tab_pair, 
     const QParams q = qparams_of(f, s, a);
     double* out = tab + 4 * tab_off[t];
     const int len = tab_len[t];
-    for (int n = threadIdx.x; n < len; n += blockDim.x) {
-        const double sr = (double)serv_rate(q, n + 1);
-        const Recip r = make_recip(sr);
-        out[4 * n + 0] = sr;
-        out[4 * n + 1] = r.yh;
-        out[4 * n + 2] = r.yl;
-    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* l = ls ? ls + tab_off[t] + t : nullptr;  // len + 1 entries per table
+    // forward sweep in tiles of 128: entries + exclusive prefix sum of log2(servRate)
+    if (threadIdx.x == 0) carry_s = 0.0;
     __syncthreads();
-    if (threadIdx.x == 0) {  // suffix minimum (a NaN rate poisons it to 0 = early exit disabled)
-        double m = out[4 * (len - 1)];
-        for (int n = len - 1; n >= 0; --n) {
-            const double v = out[4 * n];
-            m = (v < m) ? v : ((v >= m) ? m : 0.0);
-            out[4 * n + 3] = m;
+    for (int base = 0; base < len; base += blockDim.x) {
+        const int n = base + threadIdx.x;
+        double lg = 0.0;
+        if (n < len) {
+            const float srf = serv_rate(q, n + 1);
+            const double sr = (double)srf;
+            const Recip r = make_recip(sr);
+            out[4 * n + 0] = sr;
+            out[4 * n + 1] = r.yh;
+            out[4 * n + 2] = r.yl;
+            lg = (double)log2f(srf);
+        }
+        double inc = lg;  // inclusive warp scan
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        double off = carry_s;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        if (l && n < len) l[n] = (float)(off + inc - lg);
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = off + inc;
+        __syncthreads();
+    }
+    if (l && threadIdx.x == 0) l[len] = (float)carry_s;
+    // backward sweep: suffix minimum of servRate (a NaN rate poisons it to 0 = early exit disabled)
+    __shared__ double wmin[4];
+    __shared__ double carry_m;
+    if (threadIdx.x == 0) carry_m = out[4 * (len - 1)];
+    __syncthreads();
+    for (int base = 0; base < len; base += blockDim.x) {
+        const int n = len - 1 - (base + threadIdx.x);  // thread 0 takes the last entry
+        double v = n >= 0 ? out[4 * n] : 1.7976931348623157e308;
+        if (!(v == v)) v = 0.0;
+        double m = v;  // inclusive scan of min over lower thread ids (= higher n)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, m, d);
+            if (lane >= d) m = fmin(m, o);
+        }
+        if (lane == 31) wmin[warp] = m;
+        __syncthreads();
+        double pre = carry_m;
+        for (int w = 0; w < warp; ++w) pre = fmin(pre, wmin[w]);
+        m = fmin(m, pre);
+        if (n >= 0) out[4 * n + 3] = m;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_m = m;
+        __syncthreads();
+    }
+    if (pb) {
+        const float l2s0 = log2f((float)out[0]);
+        for (int bi = threadIdx.x; bi < B; bi += blockDim.x) {
+            const int b = batch[bi];
+            const float sN = (float)out[4 * (b - 1)];
+            pb[(size_t)t * B + bi] = make_float4(rate_max_of(sN), log2f(sN), l[b - 1], l2s0);
         }
     }
-    if (threadIdx.x == 32 && ls) {  // prefix sum of log2(servRate) (scheduling heuristic only)
-        float* l = ls + tab_off[t] + t;  // len + 1 entries per table
-        double acc = 0.0;
-        for (int n = 0; n <= len; ++n) {
-            l[n] = (float)acc;
-            if (n < len) acc += (double)log2f((float)out[4 * n]);
-        }
-    }
+}
+
+__global__ void grid_rates(DevFleet f, const int* __restrict__ replicas, int R, float4* __restrict__ rt) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= f.S * R) return;
+    const int s = k / R, ri = k % R;
+    const float rate = __fdiv_rn(total_rate_of(f, s), (float)replicas[ri]);
+    const float lambda = __fdiv_rn(rate, 1000.0f);
+    rt[k] = make_float4(rate, lambda, log2f(lambda), 0.0f);
 }
 
 // ---------------------------------------------------------------------------
@@ -244,7 +303,9 @@ struct GridArgs {
     const double* tab;       // shared head tables
     const float* ls;         // prefix log2 sums (estimate only)
     const long long* pair_tab_off;  // [S*A] entry offset of the pair's table (-1: none)
-    const int* pair_tab_idx;        // [S*A] table index (for the ls column)
+    const int* pair_tab_idx;        // [S*A] table index (for the ls / pb columns)
+    const float4* pb;               // [n_tab * B] per (table, batch): rmax, log2 sN, ls[N-1], log2 s0
+    const float4* rt;               // [S * R] per (server, replica): rate, lambda, log2 lambda
     long long n_cells;
     uint8_t* keys;           // [n_cells] length class
     unsigned* block_hist;    // [n_blocks * 256]
@@ -269,13 +330,11 @@ __device__ __forceinline__ void decode_cell(const GridArgs& g, long long cell, i
 
 // Estimated number of chain states before exact early termination (scheduling only; any
 // value is correct, a good one makes the 32 lanes of a warp finish together).
-__device__ __forceinline__ float estimate_len(const double* tab, const float* ls, int N, int K, float lambda) {
-    const float l2lam = log2f(lambda);
-    const float l2s0 = log2f((float)tab[0]);
-    const float l2sN = log2f((float)tab[4 * (N - 1)]);
+__device__ __forceinline__ float estimate_len(const double* tab, const float* ls, int N, int K, float lambda,
+                                              float l2lam, float l2s0, float l2sN, float lsNm1) {
     const float thr = -78.0f + fminf(0.0f, l2lam - l2s0);
-    const float d = l2sN - l2lam;                       // tail decay per state (> 0 when analysable)
-    const float L0 = (float)(N - 1) * l2lam - ls[N - 1];  // log2 p[N-1]
+    const float d = l2sN - l2lam;                     // tail decay per state (> 0 when analysable)
+    const float L0 = (float)(N - 1) * l2lam - lsNm1;  // log2 p[N-1]
     float est;
     if (L0 >= thr || N == 1) {
         est = (float)(N - 1) + (L0 - thr) / fmaxf(d, 1e-9f) + 2.0f;
@@ -317,12 +376,11 @@ __global__ void __launch_bounds__(256) grid_estimate(GridArgs g) {
         if (toff >= 0) {
             const int b = g.batch[bi];
             const int K = b + b * f.ratio;
-            const double* tab = g.tab + 4 * toff;
-            const float rmax = rate_max_of((float)tab[4 * (b - 1)]);
-            const float rate = __fdiv_rn(total_rate_of(f, s), (float)g.replicas[ri]);
-            if (!(rate <= 0.0f) && !(rate > rmax) && K >= 2) {  // Analyze: queueanalyzer.go:135-143
-                const float* ls = g.ls + toff + g.pair_tab_idx[s * f.A + a];
-                key = length_class(estimate_len(tab, ls, b, K, __fdiv_rn(rate, 1000.0f)));
+            const int t = g.pair_tab_idx[s * f.A + a];
+            const float4 pb = g.pb[(size_t)t * g.B + bi];
+            const float4 rt = g.rt[s * g.R + ri];
+            if (!(rt.x <= 0.0f) && !(rt.x > pb.x) && K >= 2) {  // Analyze: queueanalyzer.go:135-143
+                key = length_class(estimate_len(g.tab + 4 * toff, g.ls + toff + t, b, K, rt.y, rt.z, pb.w, pb.y, pb.z));
             }
         }
         g.keys[cell] = (uint8_t)key;
@@ -336,10 +394,22 @@ __global__ void __launch_bounds__(256) grid_estimate(GridArgs g) {
 __global__ void __launch_bounds__(256) grid_scan(GridArgs g, int n_blocks) {
     __shared__ unsigned total[kClasses];
     const int c = threadIdx.x;
+    unsigned* __restrict__ hist = g.block_hist;
     unsigned run = 0;
-    for (int b = 0; b < n_blocks; ++b) {
-        const unsigned v = g.block_hist[(size_t)b * kClasses + c];
-        g.block_hist[(size_t)b * kClasses + c] = run;
+    int b = 0;
+    for (; b + 8 <= n_blocks; b += 8) {  // 8 independent loads in flight per thread
+        unsigned v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = hist[(size_t)(b + u) * kClasses + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            hist[(size_t)(b + u) * kClasses + c] = run;
+            run += v[u];
+        }
+    }
+    for (; b < n_blocks; ++b) {
+        const unsigned v = hist[(size_t)b * kClasses + c];
+        hist[(size_t)b * kClasses + c] = run;
         run += v;
     }
     total[c] = run;
@@ -396,11 +466,12 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     int s, a, bi, ri;
     decode_cell(g, cell, s, a, bi, ri);
     const int b = g.batch[bi], r = g.replicas[ri];
-    const double* tab = g.tab + 4 * g.pair_tab_off[s * f.A + a];
+    const int pair = s * f.A + a;
+    const double* tab = g.tab + 4 * g.pair_tab_off[pair];
     const int N = b, K = b + b * f.ratio;
-    const float rmax = rate_max_of((float)tab[4 * (b - 1)]);
-    const float rate = __fdiv_rn(total_rate_of(f, s), (float)r);
-    const float lambda = __fdiv_rn(rate, 1000.0f);
+    const float rmax = g.pb[(size_t)g.pair_tab_idx[pair] * g.B + bi].x;
+    const float4 rt = g.rt[s * g.R + ri];
+    const float rate = rt.x, lambda = rt.y;
     ModelStats st;
     const int rc = solve_shared(tab, N, K, lambda, st);
     if (rc != kSolveOk) {
