@@ -674,16 +674,15 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     plan->n_cells = (size_t)n_cells;
     plan->n_blocks = (int)((n_cells + kSortChunk - 1) / kSortChunk);
     const size_t nc = std::max<size_t>(plan->n_cells, 1);
-    // sort workspace: keys u8 | order u32 | block histograms | class bases
-    const size_t ws = align_up(nc) + align_up(4 * nc) + align_up(4 * (size_t)std::max(plan->n_blocks, 1) * kClasses) +
-                      align_up(4 * (kClasses + 1));
+    // sort workspace: order u32 [n_cells] | items u64 | items_sorted u64 | item counter
+    const size_t max_items = (nc + 31) / 32 + (size_t)std::max(plan->n_blocks, 1);
+    const size_t ws = align_up(4 * nc) + 2 * align_up(8 * max_items) + 4 * (2 * kClasses + 8);
     CK(h->d_sort.ensure(ws));
     char* w = (char*)h->d_sort.p;
-    g.keys = (uint8_t*)w;
-    g.order = (unsigned*)(w + align_up(nc));
-    g.block_hist = (unsigned*)(w + align_up(nc) + align_up(4 * nc));
-    g.class_base = (unsigned*)(w + align_up(nc) + align_up(4 * nc) +
-                               align_up(4 * (size_t)std::max(plan->n_blocks, 1) * kClasses));
+    g.order = (unsigned*)w;
+    g.items = (unsigned long long*)(w + align_up(4 * nc));
+    g.items_sorted = (unsigned long long*)(w + align_up(4 * nc) + align_up(8 * max_items));
+    g.item_count = (unsigned*)(w + align_up(4 * nc) + 2 * align_up(8 * max_items));
     const size_t n_best = std::max<size_t>((size_t)S * A * R, 1);
     CK(h->d_best.ensure(sizeof(int) * n_best));
     g.best_rank = (int*)h->d_best.p;
@@ -713,12 +712,16 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
     if (plan.n_cells > 0) {
         CK(cudaMemsetAsync(g.cells.flags, 0, plan.n_cells, h->stream));
         fill_int<<<(unsigned)((n_best + 255) / 256), 256, 0, h->stream>>>(g.best_rank, n_best, INT_MAX);
-        grid_estimate<<<plan.n_blocks, 256, 0, h->stream>>>(g);
-        grid_scan<<<1, 256, 0, h->stream>>>(g, plan.n_blocks);
-        grid_scatter<<<plan.n_blocks, 256, 0, h->stream>>>(g);
-        const unsigned blocks = (unsigned)((plan.n_cells + 255) / 256);
+        CK(cudaMemsetAsync(g.item_count, 0, sizeof(unsigned) * (2 * kClasses + 1), h->stream));
+        grid_sort_local<<<plan.n_blocks, kSortThreads, 0, h->stream>>>(g);
+        // one warp per item; the item count lives on the device, so launch for the worst case
+        const size_t max_items = (plan.n_cells + 31) / 32 + (size_t)plan.n_blocks;
+        grid_items_scan<<<1, 256, 0, h->stream>>>(g);
+        grid_items_scatter<<<(unsigned)((max_items + 255) / 256), 256, 0, h->stream>>>(g);
+        h->launches++;
+        const unsigned blocks = (unsigned)((max_items * 32 + 255) / 256);
         grid_kernel<<<blocks, 256, 0, h->stream>>>(g);
-        h->launches += 5;
+        h->launches += 4;
     }
     CK(cudaEventRecord(h->ev_k1, h->stream));
     if (plan.n_cells > 0) {
@@ -1088,8 +1091,7 @@ long long wva_dbg_read_cycles(wva_handle* h, unsigned* cycles, unsigned* cells, 
     if (!h || !h->d_dbg.p) return 0;
     const long long n = std::min<long long>((long long)h->dbg_n, cap);
     cudaMemcpy(cycles, h->d_dbg.p, sizeof(unsigned) * n, cudaMemcpyDeviceToHost);
-    char* w = (char*)h->d_sort.p;
-    cudaMemcpy(cells, w + align_up(std::max<size_t>(h->dbg_n, 1)), sizeof(unsigned) * n, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cells, h->d_sort.p, sizeof(unsigned) * n, cudaMemcpyDeviceToHost);
     return n;
 }
 

@@ -291,7 +291,8 @@ struct CellCols {
     uint8_t* flags;  // bit0: Analyze ok, bit1: SLO-feasible
     float *ttft, *itl, *rho, *throughput;
 };
-constexpr int kSortChunk = 4096;   // cells per block in the counting sort
+constexpr int kSortChunk = 8192;   // cells per CTA in the local counting sort
+constexpr int kSortThreads = 512;
 constexpr int kClasses = 256;      // 8-bit length classes; class 255 = not analysable
 struct GridArgs {
     DevFleet f;
@@ -307,10 +308,10 @@ struct GridArgs {
     const float4* pb;               // [n_tab * B] per (table, batch): rmax, log2 sN, ls[N-1], log2 s0
     const float4* rt;               // [S * R] per (server, replica): rate, lambda, log2 lambda
     long long n_cells;
-    uint8_t* keys;           // [n_cells] length class
-    unsigned* block_hist;    // [n_blocks * 256]
-    unsigned* class_base;    // [256] (+1: number of analysable cells)
-    unsigned* order;         // [n_cells] cell ids, longest chains first
+    unsigned* order;         // [n_cells] cell ids, sorted by length class inside each chunk of kSortChunk cells
+    unsigned long long* items;         // warp work items (start | count << 32 | class << 40), unsorted
+    unsigned long long* items_sorted;  // the same, longest class first
+    unsigned* item_count;    // [0] number of items, [1..256] items per class, [257..512] class cursors
     int* best_rank;          // [S*A*R] smallest feasible batch rank (INT_MAX: none)
     CellCols cells;          // internal per-cell columns (ttft, itl, rho always present)
     int* fb_count;           // cells that need the stored-vector fallback
@@ -320,12 +321,17 @@ struct GridArgs {
 };
 
 __device__ __forceinline__ void decode_cell(const GridArgs& g, long long cell, int& s, int& a, int& bi, int& ri) {
-    ri = (int)(cell % g.R);
-    long long t = cell / g.R;
-    bi = (int)(t % g.B);
-    t /= g.B;
-    a = (int)(t % g.f.A);
-    s = (int)(t / g.f.A);
+    unsigned t = (unsigned)cell;  // n_cells < 2^32 (checked on the host): 32-bit divisions
+    const unsigned R = (unsigned)g.R, B = (unsigned)g.B, A = (unsigned)g.f.A;
+    unsigned q = t / R;
+    ri = (int)(t - q * R);
+    t = q;
+    q = t / B;
+    bi = (int)(t - q * B);
+    t = q;
+    q = t / A;
+    a = (int)(t - q * A);
+    s = (int)q;
 }
 
 // Estimated number of chain states before exact early termination (scheduling only; any
@@ -360,15 +366,36 @@ __device__ __forceinline__ int length_class(float est) {  // 0 = longest ... 254
     return 254 - min(max(c, 0), 254);
 }
 
-__global__ void __launch_bounds__(256) grid_estimate(GridArgs g) {
+// Warp-aggregated shared-memory counter: returns this lane's slot among the lanes that
+// increment the same counter (one atomic per distinct counter per warp).
+__device__ __forceinline__ unsigned agg_inc(unsigned* counters, int key) {
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    const int leader = __ffs(peers) - 1;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&counters[key], (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+// Estimate + LOCAL counting sort, one CTA per chunk of kSortChunk consecutive cells (cells of
+// one or two (server, accelerator) pairs): length classes are computed into shared memory,
+// histogrammed, scanned and scattered without leaving the CTA.  Each run of 32 sorted cells
+// becomes one warp work item tagged with its (longest) class; grid_sort_items then orders the
+// items globally, so the launch is longest-first while a pair's cells stay adjacent.
+__global__ void __launch_bounds__(kSortThreads) grid_sort_local(GridArgs g) {
+    __shared__ uint8_t keys[kSortChunk];
+    __shared__ uint8_t sorted_keys[kSortChunk];
     __shared__ unsigned hist[kClasses];
+    __shared__ unsigned cursor[kClasses];
+    __shared__ unsigned item_base;
     const DevFleet& f = g.f;
-    hist[threadIdx.x] = 0;
+    if (threadIdx.x < kClasses) hist[threadIdx.x] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * kSortChunk;
-    for (int k = threadIdx.x; k < kSortChunk; k += blockDim.x) {
+    const int n_here = (int)min((long long)kSortChunk, g.n_cells - base);
+    for (int k = threadIdx.x; k < n_here; k += kSortThreads) {
         const long long cell = base + k;
-        if (cell >= g.n_cells) break;
         int s, a, bi, ri;
         decode_cell(g, cell, s, a, bi, ri);
         int key = 255;
@@ -383,58 +410,65 @@ __global__ void __launch_bounds__(256) grid_estimate(GridArgs g) {
                 key = length_class(estimate_len(g.tab + 4 * toff, g.ls + toff + t, b, K, rt.y, rt.z, pb.w, pb.y, pb.z));
             }
         }
-        g.keys[cell] = (uint8_t)key;
-        atomicAdd(&hist[key], 1u);
+        keys[k] = (uint8_t)key;
+        agg_inc(hist, key);
     }
     __syncthreads();
-    g.block_hist[(size_t)blockIdx.x * kClasses + threadIdx.x] = hist[threadIdx.x];
-}
-
-// one thread per class: running offsets over blocks, then class bases
-__global__ void __launch_bounds__(256) grid_scan(GridArgs g, int n_blocks) {
-    __shared__ unsigned total[kClasses];
-    const int c = threadIdx.x;
-    unsigned* __restrict__ hist = g.block_hist;
-    unsigned run = 0;
-    int b = 0;
-    for (; b + 8 <= n_blocks; b += 8) {  // 8 independent loads in flight per thread
-        unsigned v[8];
+    if (threadIdx.x < 32) {  // exclusive scan of the 256 class counts by one warp
+        unsigned run = 0;
+        for (int c0 = 0; c0 < kClasses; c0 += 32) {
+            const unsigned v = hist[c0 + threadIdx.x];
+            unsigned inc = v;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = hist[(size_t)(b + u) * kClasses + c];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            hist[(size_t)(b + u) * kClasses + c] = run;
-            run += v[u];
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((int)threadIdx.x >= d) inc += o;
+            }
+            cursor[c0 + threadIdx.x] = run + inc - v;
+            run += __shfl_sync(0xffffffffu, inc, 31);
         }
     }
-    for (; b < n_blocks; ++b) {
-        const unsigned v = hist[(size_t)b * kClasses + c];
-        hist[(size_t)b * kClasses + c] = run;
-        run += v;
-    }
-    total[c] = run;
     __syncthreads();
-    if (c == 0) {
+    const int n_active = (int)cursor[255];  // class 255 (not analysable) sorts last
+    for (int k = threadIdx.x; k < n_here; k += kSortThreads) {
+        const int key = keys[k];
+        const unsigned pos = agg_inc(cursor, key);
+        g.order[base + pos] = (unsigned)(base + k);
+        sorted_keys[pos] = (uint8_t)key;
+    }
+    const int n_items = (n_active + 31) >> 5;
+    if (threadIdx.x == 0) item_base = n_items ? atomicAdd(g.item_count, (unsigned)n_items) : 0u;
+    __syncthreads();
+    for (int w = threadIdx.x; w < n_items; w += kSortThreads) {
+        const unsigned start = (unsigned)(base + 32 * w);
+        const unsigned cnt = (unsigned)min(32, n_active - 32 * w);
+        const int cls = sorted_keys[32 * w];
+        g.items[item_base + w] = (unsigned long long)start | ((unsigned long long)cnt << 32) |
+                                 ((unsigned long long)cls << 40);
+        agg_inc(g.item_count + 1, cls);  // global items-per-class histogram (warp-aggregated)
+    }
+}
+
+// Global order of the warp items by class (longest first): class cursors from the global
+// histogram, then a multi-CTA scatter with warp-aggregated atomics.
+__global__ void __launch_bounds__(256) grid_items_scan(GridArgs g) {
+    __shared__ unsigned tot[kClasses];
+    tot[threadIdx.x] = g.item_count[1 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
         unsigned acc = 0;
-        for (int k = 0; k < kClasses; ++k) {
-            g.class_base[k] = acc;
-            acc += total[k];
+        for (int c = 0; c < kClasses; ++c) {
+            g.item_count[1 + kClasses + c] = acc;
+            acc += tot[c];
         }
-        g.class_base[kClasses] = acc - total[255];  // analysable cells
     }
 }
-
-__global__ void __launch_bounds__(256) grid_scatter(GridArgs g) {
-    __shared__ unsigned cursor[kClasses];
-    cursor[threadIdx.x] = g.class_base[threadIdx.x] + g.block_hist[(size_t)blockIdx.x * kClasses + threadIdx.x];
-    __syncthreads();
-    const long long base = (long long)blockIdx.x * kSortChunk;
-    for (int k = threadIdx.x; k < kSortChunk; k += blockDim.x) {
-        const long long cell = base + k;
-        if (cell >= g.n_cells) break;
-        const unsigned pos = atomicAdd(&cursor[g.keys[cell]], 1u);
-        g.order[pos] = (unsigned)cell;
-    }
+__global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
+    const unsigned n = *g.item_count;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long it = g.items[i];
+    g.items_sorted[agg_inc(g.item_count + 1 + kClasses, (int)((it >> 40) & 0xff))] = it;
 }
 
 // SLO feasibility of an analysed cell (the build's grid semantics)
@@ -458,11 +492,13 @@ __device__ __forceinline__ void store_cell(const GridArgs& g, long long cell, in
 
 __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const DevFleet& f = g.f;
-    const unsigned n_active = g.class_base[kClasses];
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_active) return;
+    const unsigned w = idx >> 5, lane = idx & 31;
+    if (w >= *g.item_count) return;
+    const unsigned long long item = g.items_sorted[w];
+    if (lane >= (unsigned)((item >> 32) & 0xff)) return;
     const long long t_start = g.dbg_cycles ? clock64() : 0;
-    const long long cell = g.order[idx];
+    const long long cell = g.order[(unsigned)item + lane];
     int s, a, bi, ri;
     decode_cell(g, cell, s, a, bi, ri);
     const int b = g.batch[bi], r = g.replicas[ri];
@@ -647,10 +683,15 @@ __device__ int binary_search(Solver& sv, const QParams& q, int which, float xmin
         xs = __fmul_rn(0.5f, __fadd_rn(xmin, xmax));
         if (eval_target(sv, q, which, xs, ys)) return 2;
         if (within_tolerance(ys, ytarget, 1e-6f)) break;
+        const float pmin = xmin, pmax = xmax;
         if ((increasing && ytarget < ys) || (!increasing && ytarget > ys))
             xmax = xs;
         else
             xmin = xs;
+        // Fixed point: the iteration is a deterministic function of (xmin, xmax), so once an
+        // iteration leaves both bounds unchanged (the float32 interval has collapsed) the
+        // reference's remaining iterations repeat the same solve and return the same xStar.
+        if (xmin == pmin && xmax == pmax) break;
     }
     xstar = xs;
     return 0;
