@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cfloat>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -737,6 +738,275 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
     return WVA_OK;
 }
 
+
+// ---- limited mode: SolveGreedy on the host over device-computed candidates --------------
+// pkg/solver/greedy.go:35-341.  The candidate generation (the expensive part) ran on the
+// device; the greedy pass is inherently sequential over a shared capacity map (SURVEY.md
+// §8e), so it stays on the host.  Sorts are stable (the reference's pdqsort is not): ties
+// resolve by server id / accelerator id.
+struct HostCand {
+    uint8_t feasible;
+    int acc, replicas, batch;
+    float cost, value, itl, ttft, rho, max_rate;
+};
+
+struct GreedyEntry {  // greedy.go:16-22
+    int server, priority, cur = 0;
+    std::vector<int> accs;  // candidate accelerator ids ordered by value
+    float delta = 0.f;
+};
+
+inline int cmp_f32(float a, float b) {  // cmp.Compare: NaN sorts first
+    const bool an = a != a, bn = b != b;
+    if (an || bn) return an && bn ? 0 : (an ? -1 : 1);
+    return a < b ? -1 : (a > b ? 1 : 0);
+}
+
+class GreedySolver {
+  public:
+    GreedySolver(const HostFleet& f, std::vector<HostCand>& cand, std::vector<HostCand>& win)
+        : f_(f), cand_(cand), win_(win), avail_(f.type_capacity.begin(), f.type_capacity.end()) {}
+
+    void run() {
+        const int S = f_.S, A = f_.A;
+        std::vector<GreedyEntry> pool;
+        pool.reserve(S);
+        for (int s = 0; s < S; ++s) {
+            win_[s] = HostCand{};
+            win_[s].acc = WVA_ACC_NONE;
+            GreedyEntry e;
+            e.server = s;
+            e.priority = f_.srv_priority[s];
+            for (int a = 0; a < A; ++a)
+                if (at(s, a).feasible) e.accs.push_back(a);
+            if (e.accs.empty()) continue;
+            std::stable_sort(e.accs.begin(), e.accs.end(),
+                             [&](int x, int y) { return cmp_f32(at(s, x).value, at(s, y).value) < 0; });
+            e.delta = e.accs.size() > 1 ? at(s, e.accs[1]).value - at(s, e.accs[0]).value : FLT_MAX;
+            pool.push_back(std::move(e));
+        }
+        std::vector<GreedyEntry*> entries;
+        for (auto& e : pool) entries.push_back(&e);
+        std::stable_sort(entries.begin(), entries.end(),
+                         [&](GreedyEntry* x, GreedyEntry* y) { return order(*x, *y) < 0; });
+        if (f_.delayed_best_effort) {
+            std::vector<GreedyEntry*> un = allocate(entries);
+            best_effort(un);
+        } else {
+            size_t i = 0;
+            while (i < entries.size()) {  // makePriorityGroups :321-341
+                size_t j = i + 1;
+                while (j < entries.size() && entries[j]->priority == entries[i]->priority) ++j;
+                std::vector<GreedyEntry*> group(entries.begin() + i, entries.begin() + j);
+                std::vector<GreedyEntry*> un = allocate(group);
+                best_effort(un);
+                i = j;
+            }
+        }
+    }
+
+  private:
+    HostCand& at(int s, int a) { return cand_[(size_t)s * f_.A + a]; }
+    HostCand& cur(const GreedyEntry& e) { return at(e.server, e.accs[e.cur]); }
+    int units(int s, int a) const {
+        const int c = f_.perf_acc_count[(size_t)f_.srv_model[s] * f_.A + a];
+        return (c <= 0 ? 1 : c) * f_.acc_mult[a];
+    }
+    int order(GreedyEntry& a, GreedyEntry& b) {  // greedy.go:76-85
+        if (a.priority != b.priority) return a.priority < b.priority ? -1 : 1;
+        if (a.delta == b.delta) return cmp_f32(cur(b).value, cur(a).value);
+        return cmp_f32(b.delta, a.delta);
+    }
+    std::vector<GreedyEntry*> allocate(std::vector<GreedyEntry*> q) {  // greedy.go:107-166
+        std::vector<GreedyEntry*> un;
+        size_t head = 0;
+        while (head < q.size()) {
+            GreedyEntry* top = q[head++];
+            if (top->accs.empty()) continue;
+            HostCand& al = cur(*top);
+            const int g = al.acc;
+            if (g < 0 || g >= f_.A) continue;  // accelerator "" (zero-replica allocation)
+            const int t = f_.acc_type[g];
+            const int count = al.replicas * units(top->server, g);
+            if (avail_[t] >= count) {
+                avail_[t] -= count;
+                win_[top->server] = al;
+                continue;
+            }
+            top->cur++;
+            if (top->cur + 1 < (int)top->accs.size()) {
+                top->delta = at(top->server, top->accs[top->cur + 1]).value - cur(*top).value;
+            } else if (top->cur == (int)top->accs.size()) {
+                un.push_back(top);
+                continue;
+            } else {
+                top->delta = FLT_MAX;
+            }
+            // slices.BinarySearchFunc: leftmost position whose element does not order before top
+            auto it = std::partition_point(q.begin() + head, q.end(), [&](GreedyEntry* e) { return order(*e, *top) < 0; });
+            q.insert(it, top);
+        }
+        return un;
+    }
+    void scale_to(HostCand& al, int replicas) {  // greedy.go:206-211
+        const float factor = (float)replicas / (float)al.replicas;
+        al.cost *= factor;
+        al.value *= factor;
+        al.replicas = replicas;
+    }
+    void allocate_maximally(const std::vector<GreedyEntry*>& es) {  // greedy.go:194-223
+        for (GreedyEntry* e : es)
+            for (int a : e->accs) {
+                HostCand& al = at(e->server, a);
+                if (al.acc < 0 || al.acc >= f_.A) continue;
+                const int upr = units(e->server, al.acc);
+                if (upr <= 0) continue;
+                const int t = f_.acc_type[al.acc];
+                const int mx = std::min(avail_[t] / upr, al.replicas);
+                if (mx > 0) {
+                    scale_to(al, mx);
+                    win_[e->server] = al;
+                    avail_[t] -= mx * upr;
+                    break;
+                }
+            }
+    }
+    void allocate_equally(const std::vector<GreedyEntry*>& es) {  // greedy.go:239-316
+        struct Ticket {
+            bool present = true, active = false, allocated = false;
+            int type = 0, upr = 0, n = 0;
+            HostCand* fin = nullptr;
+        };
+        std::vector<Ticket> tk(es.size());
+        size_t live = es.size();
+        while (live > 0) {
+            for (size_t k = 0; k < es.size(); ++k) {
+                Ticket& t = tk[k];
+                if (!t.present) continue;
+                if (!t.active) {
+                    for (int a : es[k]->accs) {
+                        HostCand& al = at(es[k]->server, a);
+                        if (al.acc < 0 || al.acc >= f_.A) continue;
+                        const int upr = units(es[k]->server, al.acc);
+                        if (upr > 0 && avail_[f_.acc_type[al.acc]] >= upr) {
+                            t.active = true;
+                            t.type = f_.acc_type[al.acc];
+                            t.upr = upr;
+                            t.fin = &al;
+                            break;
+                        }
+                    }
+                    if (!t.active) {
+                        t.present = false;
+                        --live;
+                        continue;
+                    }
+                }
+                if (std::min(avail_[t.type] / t.upr, t.fin->replicas) > 0) {
+                    t.n++;
+                    avail_[t.type] -= t.upr;
+                    t.allocated = true;
+                } else {
+                    t.present = false;
+                    --live;
+                }
+            }
+        }
+        for (size_t k = 0; k < es.size(); ++k)
+            if (tk[k].allocated) {
+                scale_to(*tk[k].fin, tk[k].n);
+                win_[es[k]->server] = *tk[k].fin;
+            }
+    }
+    void best_effort(const std::vector<GreedyEntry*>& un) {  // greedy.go:169-190
+        switch (f_.saturation_policy) {
+        case WVA_SAT_PRIORITY_EXHAUSTIVE: allocate_maximally(un); break;
+        case WVA_SAT_PRIORITY_ROUND_ROBIN: {
+            size_t i = 0;
+            while (i < un.size()) {
+                size_t j = i + 1;
+                while (j < un.size() && un[j]->priority == un[i]->priority) ++j;
+                allocate_equally(std::vector<GreedyEntry*>(un.begin() + i, un.begin() + j));
+                i = j;
+            }
+            break;
+        }
+        case WVA_SAT_ROUND_ROBIN: allocate_equally(un); break;
+        default: break;
+        }
+    }
+    const HostFleet& f_;
+    std::vector<HostCand>& cand_;
+    std::vector<HostCand>& win_;
+    std::vector<int> avail_;
+};
+
+void block_to_cands(const void* host_block, const Block& b, std::vector<HostCand>& out) {
+    const char* p = (const char*)host_block;
+    out.resize(b.n);
+    for (size_t i = 0; i < b.n; ++i) {
+        HostCand& c = out[i];
+        c.feasible = ((const uint8_t*)(p + b.off_feasible))[i];
+        c.acc = ((const int*)(p + b.off_acc))[i];
+        c.replicas = ((const int*)(p + b.off_replicas))[i];
+        c.batch = ((const int*)(p + b.off_batch))[i];
+        c.cost = ((const float*)(p + b.off_cost))[i];
+        c.value = ((const float*)(p + b.off_value))[i];
+        c.itl = ((const float*)(p + b.off_itl))[i];
+        c.ttft = ((const float*)(p + b.off_ttft))[i];
+        c.rho = ((const float*)(p + b.off_rho))[i];
+        c.max_rate = ((const float*)(p + b.off_rate))[i];
+    }
+}
+void cands_to_abi(const std::vector<HostCand>& v, wva_allocs* out) {
+    if (!out) return;
+    for (size_t i = 0; i < v.size(); ++i) {
+        const HostCand& c = v[i];
+        if (out->feasible) out->feasible[i] = c.feasible;
+        if (out->acc) out->acc[i] = c.acc;
+        if (out->replicas) out->replicas[i] = c.replicas;
+        if (out->batch) out->batch[i] = c.batch;
+        if (out->cost) out->cost[i] = c.cost;
+        if (out->value) out->value[i] = c.value;
+        if (out->itl) out->itl[i] = c.itl;
+        if (out->ttft) out->ttft[i] = c.ttft;
+        if (out->rho) out->rho[i] = c.rho;
+        if (out->max_rate) out->max_rate[i] = c.max_rate;
+    }
+}
+
+// resident analyze + greedy solve with host outputs
+int run_greedy_host(wva_handle* h, wva_allocs* candidates, wva_allocs* winners) {
+    const HostFleet& hf = h->hf;
+    for (int a = 0; a < hf.A; ++a)
+        if (hf.T <= 0 || hf.acc_type[a] < 0 || hf.acc_type[a] >= hf.T)
+            return h->fail(WVA_ERR_BAD_ARG, "limited mode needs a type id and a capacity for every accelerator");
+    const size_t n_pairs = (size_t)hf.S * hf.A;
+    const Block bc = block_layout(n_pairs), bw = block_layout(hf.S);
+    CK(h->d_cand_block.ensure(bc.bytes + 16));
+    CK(h->d_win_block.ensure(bw.bytes + 16));
+    const AllocCols dc = block_cols(h->d_cand_block.p, bc), dw = block_cols(h->d_win_block.p, bw);
+    CK(cudaEventRecord(h->ev_d0, h->stream));
+    int rc = enqueue_size(h, dc, &dw);  // the unlimited kernel also assigns value = transition penalty
+    if (rc) return rc;
+    const size_t stage_bytes = align_up(bc.bytes) + 256;
+    CK(h->out_stage.ensure(stage_bytes));
+    char* hs = (char*)h->out_stage.p;
+    if (bc.bytes) CK(cudaMemcpyAsync(hs, h->d_cand_block.p, bc.bytes, cudaMemcpyDeviceToHost, h->stream));
+    int* ctrl_host = (int*)(hs + align_up(bc.bytes));
+    CK(cudaMemcpyAsync(ctrl_host, h->d_ctrl.p, CTRL_INTS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    rc = finish_timing(h);
+    if (rc) return rc;
+    rc = check_fallback_status(h, ctrl_host, (long long)h->cand_pair.size() + 1);
+    if (rc) return rc;
+    std::vector<HostCand> cand, win((size_t)hf.S);
+    block_to_cands(hs, bc, cand);
+    GreedySolver(hf, cand, win).run();
+    cands_to_abi(cand, candidates);
+    cands_to_abi(win, winners);
+    return WVA_OK;
+}
+
 }  // namespace
 
 // =============================================================================
@@ -876,7 +1146,7 @@ int wva_resolve(wva_handle* h, wva_allocs* candidates, wva_allocs* winners) {
     if (!h || !winners) return WVA_ERR_BAD_ARG;
     CK(cudaSetDevice(h->device));
     if (!h->resident) return h->fail(WVA_ERR_STATE, "no resident fleet (call wva_upload first)");
-    if (!h->hf.unlimited) return h->fail(WVA_ERR_UNSUPPORTED, "limited (greedy) mode is not implemented yet");
+    if (!h->hf.unlimited) return run_greedy_host(h, candidates, winners);
     return run_size_host(h, candidates, winners);
 }
 
@@ -892,7 +1162,7 @@ int wva_resolve_device(wva_handle* h, wva_allocs* winners_dev) {
     if (!h || !winners_dev) return WVA_ERR_BAD_ARG;
     CK(cudaSetDevice(h->device));
     if (!h->resident) return h->fail(WVA_ERR_STATE, "no resident fleet (call wva_upload first)");
-    if (!h->hf.unlimited) return h->fail(WVA_ERR_UNSUPPORTED, "limited (greedy) mode is not implemented yet");
+    if (!h->hf.unlimited) return h->fail(WVA_ERR_UNSUPPORTED, "limited (greedy) mode has host outputs only: use wva_resolve");
     const HostFleet& hf = h->hf;
     const Block bc = block_layout((size_t)hf.S * hf.A);
     CK(h->d_cand_block.ensure(bc.bytes + 16));
