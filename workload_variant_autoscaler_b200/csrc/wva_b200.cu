@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -134,6 +135,9 @@ struct wva_handle {
     std::vector<long long> group_off;
     int size_Nmax = 0;
     DevBuf d_cand_pair, d_cand_N, d_group_off, d_ltab;
+    DevBuf d_sz_tab, d_sz_ls, d_sz_off, d_sz_state, d_sz_req, d_sz_sort;
+    PinBuf sz_pin;
+    bool size_rounds = true;  // round-based K1 (default); WVA_SIZE_MODE=thread selects one thread per candidate
     // grid path caches
     uint64_t grid_epoch = ~0ull;
     std::vector<int> grid_batch, grid_replicas;
@@ -440,9 +444,100 @@ int prepare_size(wva_handle* h) {
                                                            (const int*)h->d_cand_N.p, n,
                                                            (const long long*)h->d_group_off.p, (float*)h->d_ltab.p);
         h->launches++;
+        if (h->size_rounds) {  // one shared-format table per candidate (N entries)
+            std::vector<long long> off(n + 1, 0);
+            for (int j = 0; j < n; ++j) off[j + 1] = off[j] + h->cand_N[j];
+            CK(h->d_sz_off.ensure(sizeof(long long) * (n + 1)));
+            CK(h->d_sz_tab.ensure(sizeof(double) * 4 * (size_t)off[n] + 1024));
+            CK(h->d_sz_ls.ensure(sizeof(float) * ((size_t)off[n] + n + 1)));
+            CK(cudaMemcpyAsync(h->d_sz_off.p, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, h->stream));
+            build_pair_tables<<<n, 128, 0, h->stream>>>(h->df, (const int*)h->d_cand_pair.p, (const long long*)h->d_sz_off.p,
+                                                        (const int*)h->d_cand_N.p, n, (double*)h->d_sz_tab.p,
+                                                        (float*)h->d_sz_ls.p, nullptr, 0, nullptr);
+            h->launches++;
+        }
         CK(cudaGetLastError());
     }
     h->size_epoch = h->epoch_tokens;
+    return WVA_OK;
+}
+
+// Round-based K1: see the comment above SzArgs in wva_kernels.cuh.
+int run_size_rounds(wva_handle* h, const SizeArgs& sa, int n) {
+    const size_t n2 = 2 * (size_t)n;
+    // state block
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 16); return at; };
+    const size_t o_xmin = take(4 * n2), o_xmax = take(4 * n2), o_y0 = take(4 * n2), o_y1 = take(4 * n2), o_xs = take(4 * n2);
+    const size_t o_sst = take(n2), o_inc = take(n2), o_iter = take(n2), o_ind = take(n2), o_slot = take(4 * n2);
+    const size_t o_phase = take(n), o_rmax = take(4 * (size_t)n), o_l2s0 = take(4 * (size_t)n), o_l2sN = take(4 * (size_t)n),
+                 o_lsN = take(4 * (size_t)n), o_rstar = take(4 * (size_t)n), o_total = take(4 * (size_t)n),
+                 o_cost = take(4 * (size_t)n), o_nrep = take(8 * (size_t)n);
+    CK(h->d_sz_state.ensure(o));
+    char* sp = (char*)h->d_sz_state.p;
+    // request block (capacity 2n)
+    o = 0;
+    const size_t r_id = take(4 * n2), r_lam = take(4 * n2), r_key = take(n2), r_out = take(16 * n2), r_bail = take(n2),
+                 r_cnt = take(16);
+    CK(h->d_sz_req.ensure(o));
+    char* rp = (char*)h->d_sz_req.p;
+    // sort workspace
+    const size_t chunks = (n2 + kSortChunk - 1) / kSortChunk;
+    const size_t max_items = (n2 + 31) / 32 + chunks;
+    o = 0;
+    const size_t w_order = take(4 * n2), w_items = take(8 * max_items), w_sorted = take(8 * max_items),
+                 w_cnt = take(4 * (2 * kClasses + 8));
+    CK(h->d_sz_sort.ensure(o));
+    char* wp = (char*)h->d_sz_sort.p;
+    CK(h->sz_pin.ensure(64));
+
+    SzArgs g{};
+    g.f = sa.f;
+    g.cand_pair = sa.cand_pair;
+    g.cand_N = sa.cand_N;
+    g.n_cand = n;
+    g.tab = (const double*)h->d_sz_tab.p;
+    g.tab_off = (const long long*)h->d_sz_off.p;
+    g.ls = (const float*)h->d_sz_ls.p;
+    g.xmin = (float*)(sp + o_xmin); g.xmax = (float*)(sp + o_xmax); g.y0 = (float*)(sp + o_y0); g.y1 = (float*)(sp + o_y1);
+    g.xs = (float*)(sp + o_xs);
+    g.sst = (uint8_t*)(sp + o_sst); g.inc = (uint8_t*)(sp + o_inc); g.iter = (uint8_t*)(sp + o_iter);
+    g.ind = (int8_t*)(sp + o_ind); g.slot = (int*)(sp + o_slot);
+    g.phase = (uint8_t*)(sp + o_phase);
+    g.rmax = (float*)(sp + o_rmax); g.l2s0 = (float*)(sp + o_l2s0); g.l2sN = (float*)(sp + o_l2sN); g.lsN = (float*)(sp + o_lsN);
+    g.rate_star = (float*)(sp + o_rstar); g.total_rate = (float*)(sp + o_total); g.cost = (float*)(sp + o_cost);
+    g.nrep = (long long*)(sp + o_nrep);
+    g.req_id = (unsigned*)(rp + r_id); g.req_lam = (float*)(rp + r_lam); g.req_key = (uint8_t*)(rp + r_key);
+    g.req_out = (float4*)(rp + r_out); g.req_bail = (uint8_t*)(rp + r_bail); g.n_req = (unsigned*)(rp + r_cnt);
+    g.ws.order = (unsigned*)(wp + w_order); g.ws.items = (unsigned long long*)(wp + w_items);
+    g.ws.items_sorted = (unsigned long long*)(wp + w_sorted); g.ws.item_count = (unsigned*)(wp + w_cnt);
+    g.cand = sa.cand;
+    g.fb_count = sa.fb_count; g.fb_list = sa.fb_list; g.fb_cap = sa.fb_cap;
+
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    sz_init<<<nb, 256, 0, h->stream>>>(g);
+    h->launches++;
+    unsigned* pin = (unsigned*)h->sz_pin.p;
+    // at most 1 + 102 evaluations per search, then two Analyze rounds, then the final consume
+    for (int round = 0; round < 112; ++round) {
+        CK(cudaMemsetAsync(g.n_req, 0, sizeof(unsigned), h->stream));
+        CK(cudaMemsetAsync(g.ws.item_count, 0, sizeof(unsigned) * (2 * kClasses + 1), h->stream));
+        sz_advance<<<nb, 256, 0, h->stream>>>(g);
+        h->launches++;
+        // the request count decides whether another round is needed
+        CK(cudaMemcpyAsync(pin, g.n_req, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const unsigned n_req = *pin;
+        if (n_req == 0) break;
+        const unsigned cks = (n_req + kSortChunk - 1) / kSortChunk;
+        const unsigned items_max = (n_req + 31) / 32 + cks;
+        sz_sort_local<<<cks, kSortThreads, 0, h->stream>>>(g);
+        ws_items_scan<<<1, 256, 0, h->stream>>>(g.ws);
+        ws_items_scatter<<<(items_max + 255) / 256, 256, 0, h->stream>>>(g.ws);
+        sz_solve<<<(items_max * 32 + 255) / 256, 256, 0, h->stream>>>(g);
+        h->launches += 4;
+    }
+    CK(cudaGetLastError());
     return WVA_OK;
 }
 
@@ -472,7 +567,10 @@ int enqueue_size(wva_handle* h, const AllocCols& cand, const AllocCols* winners)
     g.fb_list = (int*)h->d_fb_list.p;
     g.fb_cap = std::max(n, 1);
     CK(cudaEventRecord(h->ev_k0, h->stream));
-    if (n > 0) {
+    if (n > 0 && h->size_rounds) {
+        rc = run_size_rounds(h, g, n);
+        if (rc) return rc;
+    } else if (n > 0) {
         size_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(g);
         h->launches++;
     }
@@ -1046,6 +1144,7 @@ int wva_create(wva_handle** out, int device) {
     wva_handle* h = new (std::nothrow) wva_handle();
     if (!h) return WVA_ERR_NOMEM;
     h->device = device;
+    if (const char* m = getenv("WVA_SIZE_MODE")) h->size_rounds = std::string(m) != "thread";
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1062,13 +1161,14 @@ void wva_destroy(wva_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->arena, &h->d_cand_pair, &h->d_cand_N, &h->d_group_off, &h->d_ltab, &h->d_grid_lists,
+    DevBuf* bufs[] = {&h->arena, &h->d_cand_pair, &h->d_cand_N, &h->d_group_off, &h->d_ltab, &h->d_sz_tab, &h->d_sz_ls, &h->d_sz_off, &h->d_sz_state, &h->d_sz_req, &h->d_sz_sort, &h->d_grid_lists,
                       &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_ls, &h->d_sort, &h->d_best, &h->d_pb,
                       &h->d_cand_block, &h->d_win_block, &h->d_ctrl, &h->d_fb_list, &h->d_scratch,
                       &h->d_cells, &h->d_sweep};
     for (DevBuf* b : bufs) b->release();
     h->stage.release();
     h->out_stage.release();
+    h->sz_pin.release();
     if (h->ev_k0) cudaEventDestroy(h->ev_k0);
     if (h->ev_k1) cudaEventDestroy(h->ev_k1);
     if (h->ev_d0) cudaEventDestroy(h->ev_d0);
