@@ -309,7 +309,12 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // Fast-window test on the high word: lo <= hi(p) < lo + span.
 #define WVA_FASTWIN(p, lo, span) ((((unsigned)__double2hiint(p)) - (lo)) < (span))
 
-__device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st) {
+// STASH > 0: the first STASH states of pass 1 are kept in shared memory (stash[(j-1)*32] for
+// state j, one 8-byte column per lane) and pass 2 reads them back instead of re-running the
+// recurrence for those states — most grid chains are shorter than that.
+template <int STASH>
+__device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st,
+                                           double* __restrict__ stash) {
     const unsigned warp_mask = __activemask();
     const double lam = (double)lambda;
     const int nh = N - 1;
@@ -332,6 +337,7 @@ __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, 
     // ---- pass 1 -----------------------------------------------------------------
     double sum = __dadd_rn(1.0, p);
     int j_end = K + 1;
+    if (STASH > 0) stash[0] = p;
     {
         int n = 1;  // p holds p[n]
         const int n_stop = bail ? 0 : K;
@@ -347,11 +353,13 @@ __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, 
                 p = div_recip(__dmul_rn(p, lam), A);
                 if (n < nh) load_recip(tab, n + 2 < nh ? n + 2 : nh, A);
                 sum = __dadd_rn(sum, p);
+                if (STASH > 0 && n < STASH) stash[n * 32] = p;  // state n+1
                 ++n;
                 if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) break;
                 p = div_recip(__dmul_rn(p, lam), B);
                 if (n < nh) load_recip(tab, n + 2 < nh ? n + 2 : nh, B);
                 sum = __dadd_rn(sum, p);
+                if (STASH > 0 && n < STASH) stash[n * 32] = p;
                 ++n;
             }
             if (n >= n_stop) break;
@@ -367,6 +375,7 @@ __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, 
             load_recip(tab, n < nh ? n : nh, A);
             p = hp >= kHiPLo ? div_recip(__dmul_rn(p, lam), A) : __ddiv_rn(__dmul_rn(p, lam), A.b);
             sum = __dadd_rn(sum, p);
+            if (STASH > 0 && n < STASH) stash[n * 32] = p;
             ++n;
         }
     }
@@ -375,12 +384,43 @@ __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, 
     if (bail) { sum = 1.0; j_end = 1; }
 
     // ---- pass 2 -----------------------------------------------------------------
-    const Recip z = make_recip(sum);
+    // reciprocal of the normalising sum: zh = RN(1/sum) must be exact, zl only needs a few
+    // correct bits (it enters at 2^-53), so RN(e*zh) replaces the second IEEE division
+    Recip z;
+    z.b = sum;
+    z.yh = __ddiv_rn(1.0, sum);
+    z.yl = __dmul_rn(__fma_rn(-sum, z.yh, 1.0), z.yh);
     double acc = 0.0, sum_p = z.yh, pn = 0.0, di = 1.0, acc_at_N = 0.0;
     p = p1;
     __syncwarp(warp_mask);
     {
         int i = 1;  // p holds p[i]
+        if (STASH > 0) {
+            // states 1..min(STASH, j_end-1) come back from shared memory: no recurrence, no table loads
+            const int i_st = (j_end - 1 < STASH) ? j_end - 1 : STASH;
+#pragma unroll 2
+            for (; i <= i_st; ++i) {
+                p = stash[(i - 1) * 32];
+                if (!WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
+                pn = div_recip(p, z);
+                acc = __dadd_rn(acc, __dmul_rn(di, pn));
+                di = __dadd_rn(di, 1.0);
+                if (i <= N) {
+                    sum_p = __dadd_rn(sum_p, pn);
+                    acc_at_N = acc;
+                }
+            }
+            // i = first state not yet accumulated; p must hold p[i] for the generic loop below
+            if (i <= i_st) {
+                // left early: p = p[i] is outside the fast window (tiny or zero): generic loop handles it
+            } else if (i < j_end) {
+                // continue the recurrence from the last stashed state: p[i] = step(p[i-1])
+                load_recip(tab, i - 1 < nh ? i - 1 : nh, A);
+                const double pprev = stash[(i - 2) * 32];
+                p = WVA_FASTWIN(pprev, kHiPLo, kHiPHi - kHiPLo) ? div_recip(__dmul_rn(pprev, lam), A)
+                                                                 : __ddiv_rn(__dmul_rn(pprev, lam), A.b);
+            }
+        }
         while (i < j_end) {
             load_recip(tab, i < nh ? i : nh, A);  // triple of the step out of state i
             load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
@@ -440,6 +480,10 @@ __device__ __noinline__ int solve_shared(const double* __restrict__ tab, int N, 
     if (w < 0.0f) w = 0.0f;
     st.avg_wait_time = w;
     return bail ? kSolveBail : kSolveOk;
+}
+
+__device__ __forceinline__ int solve_shared(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st) {
+    return solve_shared_t<0>(tab, N, K, lambda, st, nullptr);
 }
 
 // Stored-vector fallback: a literal restatement of computeProbabilities /

@@ -293,6 +293,7 @@ struct CellCols {
 };
 constexpr int kSortChunk = 8192;   // cells per CTA in the local counting sort
 constexpr int kSortThreads = 512;
+constexpr int kGridStash = 24;     // chain states kept in shared memory between the two passes (per lane)
 constexpr int kClasses = 256;      // 8-bit length classes; class 255 = not analysable
 struct GridArgs {
     DevFleet f;
@@ -509,7 +510,9 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const float4 rt = g.rt[s * g.R + ri];
     const float rate = rt.x, lambda = rt.y;
     ModelStats st;
-    const int rc = solve_shared(tab, N, K, lambda, st);
+    extern __shared__ double grid_stash[];  // [warp][state][lane]
+    double* stash = grid_stash + (size_t)(threadIdx.x >> 5) * (kGridStash * 32) + (threadIdx.x & 31);
+    const int rc = solve_shared_t<kGridStash>(tab, N, K, lambda, st, stash);
     if (rc != kSolveOk) {
         const int k = atomicAdd(g.fb_count, 1);
         if (k < g.fb_cap) g.fb_cells[k] = cell;
