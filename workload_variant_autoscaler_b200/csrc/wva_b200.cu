@@ -132,12 +132,11 @@ struct wva_handle {
     // size path caches
     uint64_t size_epoch = ~0ull;
     std::vector<int> cand_pair, cand_N;
-    std::vector<long long> group_off;
     int size_Nmax = 0;
-    DevBuf d_cand_pair, d_cand_N, d_group_off, d_ltab;
+    DevBuf d_cand_pair, d_cand_N;
     DevBuf d_sz_tab, d_sz_ls, d_sz_off, d_sz_state, d_sz_req, d_sz_sort;
     PinBuf sz_pin;
-    bool size_rounds = true;  // round-based K1 (default); WVA_SIZE_MODE=thread selects one thread per candidate
+
     // grid path caches
     uint64_t grid_epoch = ~0ull;
     std::vector<int> grid_batch, grid_replicas;
@@ -425,37 +424,24 @@ int prepare_size(wva_handle* h) {
     h->cand_pair = pairs;
     h->cand_N.resize(n);
     for (int j = 0; j < n; ++j) h->cand_N[j] = Ns[pairs[j]];
-    const int n_groups = (n + 31) / 32;
-    h->group_off.assign(n_groups + 1, 0);
-    for (int g = 0; g < n_groups; ++g) h->group_off[g + 1] = h->group_off[g] + (long long)h->cand_N[g * 32] * 32;
     h->size_Nmax = n ? h->cand_N[0] : 1;
     if (n) {
         CK(h->d_cand_pair.ensure(sizeof(int) * n));
         CK(h->d_cand_N.ensure(sizeof(int) * n));
-        CK(h->d_group_off.ensure(sizeof(long long) * (n_groups + 1)));
-        CK(h->d_ltab.ensure(sizeof(float) * (size_t)h->group_off[n_groups]));
         CK(cudaMemcpyAsync(h->d_cand_pair.p, h->cand_pair.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_cand_N.p, h->cand_N.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_group_off.p, h->group_off.data(), sizeof(long long) * (n_groups + 1),
-                           cudaMemcpyHostToDevice, h->stream));
-        // the host vectors above stay alive until the next prepare_size, and every
-        // entry point synchronises before returning, so pageable sources are safe here
-        build_lane_tables<<<n_groups, 256, 0, h->stream>>>(h->df, (const int*)h->d_cand_pair.p,
-                                                           (const int*)h->d_cand_N.p, n,
-                                                           (const long long*)h->d_group_off.p, (float*)h->d_ltab.p);
+        // one shared-format service-rate table per candidate (N entries), cached until the token
+        // statistics or the fleet change
+        std::vector<long long> off(n + 1, 0);
+        for (int j = 0; j < n; ++j) off[j + 1] = off[j] + h->cand_N[j];
+        CK(h->d_sz_off.ensure(sizeof(long long) * (n + 1)));
+        CK(h->d_sz_tab.ensure(sizeof(double) * 4 * (size_t)off[n] + 1024));
+        CK(h->d_sz_ls.ensure(sizeof(float) * ((size_t)off[n] + n + 1)));
+        CK(cudaMemcpyAsync(h->d_sz_off.p, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, h->stream));
+        build_pair_tables<<<n, 128, 0, h->stream>>>(h->df, (const int*)h->d_cand_pair.p, (const long long*)h->d_sz_off.p,
+                                                    (const int*)h->d_cand_N.p, n, (double*)h->d_sz_tab.p,
+                                                    (float*)h->d_sz_ls.p, nullptr, 0, nullptr);
         h->launches++;
-        if (h->size_rounds) {  // one shared-format table per candidate (N entries)
-            std::vector<long long> off(n + 1, 0);
-            for (int j = 0; j < n; ++j) off[j + 1] = off[j] + h->cand_N[j];
-            CK(h->d_sz_off.ensure(sizeof(long long) * (n + 1)));
-            CK(h->d_sz_tab.ensure(sizeof(double) * 4 * (size_t)off[n] + 1024));
-            CK(h->d_sz_ls.ensure(sizeof(float) * ((size_t)off[n] + n + 1)));
-            CK(cudaMemcpyAsync(h->d_sz_off.p, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, h->stream));
-            build_pair_tables<<<n, 128, 0, h->stream>>>(h->df, (const int*)h->d_cand_pair.p, (const long long*)h->d_sz_off.p,
-                                                        (const int*)h->d_cand_N.p, n, (double*)h->d_sz_tab.p,
-                                                        (float*)h->d_sz_ls.p, nullptr, 0, nullptr);
-            h->launches++;
-        }
         CK(cudaGetLastError());
     }
     h->size_epoch = h->epoch_tokens;
@@ -559,20 +545,15 @@ int enqueue_size(wva_handle* h, const AllocCols& cand, const AllocCols* winners)
     g.cand_pair = (const int*)h->d_cand_pair.p;
     g.cand_N = (const int*)h->d_cand_N.p;
     g.n_cand = n;
-    g.ltab = (const float*)h->d_ltab.p;
-    g.group_off = (const long long*)h->d_group_off.p;
     g.cand = cand;
     g.fb_count = (int*)h->d_ctrl.p + CTRL_FB_COUNT;
     CK(h->d_fb_list.ensure(sizeof(int) * std::max(n, 1)));
     g.fb_list = (int*)h->d_fb_list.p;
     g.fb_cap = std::max(n, 1);
     CK(cudaEventRecord(h->ev_k0, h->stream));
-    if (n > 0 && h->size_rounds) {
+    if (n > 0) {
         rc = run_size_rounds(h, g, n);
         if (rc) return rc;
-    } else if (n > 0) {
-        size_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(g);
-        h->launches++;
     }
     CK(cudaEventRecord(h->ev_k1, h->stream));
     if (n > 0) {
@@ -1145,7 +1126,6 @@ int wva_create(wva_handle** out, int device) {
     wva_handle* h = new (std::nothrow) wva_handle();
     if (!h) return WVA_ERR_NOMEM;
     h->device = device;
-    if (const char* m = getenv("WVA_SIZE_MODE")) h->size_rounds = std::string(m) != "thread";
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1162,7 +1142,7 @@ void wva_destroy(wva_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->arena, &h->d_cand_pair, &h->d_cand_N, &h->d_group_off, &h->d_ltab, &h->d_sz_tab, &h->d_sz_ls, &h->d_sz_off, &h->d_sz_state, &h->d_sz_req, &h->d_sz_sort, &h->d_grid_lists,
+    DevBuf* bufs[] = {&h->arena, &h->d_cand_pair, &h->d_cand_N, &h->d_sz_tab, &h->d_sz_ls, &h->d_sz_off, &h->d_sz_state, &h->d_sz_req, &h->d_sz_sort, &h->d_grid_lists,
                       &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_ls, &h->d_sort, &h->d_best, &h->d_pb,
                       &h->d_cand_block, &h->d_win_block, &h->d_ctrl, &h->d_fb_list, &h->d_scratch,
                       &h->d_cells, &h->d_sweep};

@@ -144,153 +144,8 @@ struct ModelStats {  // queuemodel.go:10-19 + mm1kmodel.go:15 + mm1modelstatedep
     float throughput, avg_resp_time, avg_wait_time, avg_serv_time, avg_num_in_servers;
 };
 
-// Head tables.  TAB_SHARED: one table per (server, accelerator) pair, read at the same
-// address by the lanes of a warp: 4 doubles per n {servRate[n], yh, yl, min(servRate[n..])}.
-// TAB_LANE: one float32 servRate column per lane, element n at tab[n * stride] (coalesced
-// across the warp) plus n_mono, the index from which the column is non-decreasing; the
-// head then uses the generic IEEE division.
-enum { TAB_SHARED = 0, TAB_LANE = 1 };
-
-// Is p non-increasing from state j (< N-1) on?  True when lambda is clearly below every
-// service rate the remaining steps divide by.
-template <int TAB>
-__device__ __forceinline__ bool mono_from(const void* tab, int stride, int n_mono, int j, double lam) {
-    if (TAB == TAB_SHARED)
-        return (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(((const double*)tab)[4 * j + 3]);
-    return j >= n_mono &&
-           (unsigned)__double2hiint(lam) < (unsigned)__double2hiint((double)((const float*)tab)[(size_t)j * stride]);
-}
-
-// Table access for one step: the reciprocal triple of servRate[min(n, N-1)].
-template <int TAB>
-__device__ __forceinline__ Recip step_recip(const void* tab, int stride, int n, int nh, const Recip& tail) {
-    if (TAB == TAB_SHARED) {
-        if (n < nh) {
-            const double2 t0 = *(const double2*)((const double*)tab + 4 * n);
-            Recip r;
-            r.b = t0.x;
-            r.yh = t0.y;
-            r.yl = ((const double*)tab)[4 * n + 2];
-            return r;
-        }
-        return tail;
-    }
-    Recip r = tail;
-    if (n < nh) r.b = (double)((const float*)tab)[(size_t)n * stride];
-    return r;
-}
-// One recurrence step p[n] -> p[n+1] on the fast path (p inside the window).
-template <int TAB>
-__device__ __forceinline__ double step_fast(const void* tab, int stride, int n, int nh, const Recip& tail, double a) {
-    const Recip r = step_recip<TAB>(tab, stride, n, nh, tail);
-    if (TAB == TAB_LANE && n < nh) return __ddiv_rn(a, r.b);  // no reciprocal for per-lane head rates
-    return div_recip(a, r);
-}
-
-// Returns kSolveOk / kSolveBail.  N = len(servRate), K = occupancy upper bound (>= 2),
-// tail = servRate[N-1] with its reciprocal.  Every loop is a single per-lane loop (no
-// separate head / tail code paths) so that lanes of a warp that work on different batch
-// sizes stay converged: only the trip count differs between lanes.
-template <int TAB>
-__device__ __noinline__ int solve_model(const void* tab, int stride, int n_mono, int N, int K, float lambda,
-                                        const Recip& tail_in, ModelStats& st) {
-    // Lanes enter together and leave together: no early return, explicit re-convergence
-    // after each variable-trip-count loop (otherwise lanes that finish pass 1 early run
-    // pass 2 on their own and the warp serialises).
-    const unsigned warp_mask = __activemask();
-    const Recip tail = tail_in;  // keep the tail triple in registers (the reference lives in local memory)
-    const double lam = (double)lambda;
-    bool bail = !in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail.b, kHiRateLo, kHiRateHi);
-    const int nh = N - 1;  // steps n < nh read servRate[n] from the table; the rest use the tail
-    // in the tail p is non-increasing iff lambda < servRate[N-1] (with a margin for rounding)
-    const bool tail_mono = (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tail.b);
-
-    // ---- p[1] and the negligibility threshold --------------------------------------
-    double p = bail ? 0.0 : step_fast<TAB>(tab, stride, 0, nh, tail, lam);  // RN(1*lambda) = lambda
-    if (!(p >= 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) bail = true;
-    const double p1 = p;
-    unsigned thr_hi = 0;  // early exit when hi(p) < thr_hi; 0 disables it
-    if (K < (1 << 23)) thr_hi = (unsigned)__double2hiint(__dmul_rn(fmin(1.0, p1), 0x1p-78));
-
-    // ---- pass 1: normalising sum ------------------------------------------------
-    double sum = __dadd_rn(1.0, p);
-    int j_end = K + 1;  // first state index that is skipped (K + 1: nothing skipped)
-    const int n_stop = bail ? 0 : K;
-#pragma unroll 2
-    for (int n = 1; n < n_stop; ++n) {  // p holds p[n]
-        if (in_window(p, kHiPLo, kHiPHi)) {
-            p = step_fast<TAB>(tab, stride, n, nh, tail, __dmul_rn(p, lam));
-        } else {
-            if (p == 0.0) { j_end = n + 1; break; }
-            if (!(p > 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) { bail = true; break; }
-            p = __ddiv_rn(__dmul_rn(p, lam), step_recip<TAB>(tab, stride, n, nh, tail).b);
-        }
-        sum = __dadd_rn(sum, p);
-        if ((unsigned)__double2hiint(p) < thr_hi) {  // p[n+1] is negligible: is the chain past its mode?
-            const int j = n + 1;
-            if (j >= nh ? tail_mono : mono_from<TAB>(tab, stride, n_mono, j, lam)) {
-                j_end = j + 1;
-                break;
-            }
-        }
-    }
-    __syncwarp(warp_mask);
-    if (!in_window(sum, kHiSumLo, kHiSumHi)) bail = true;
-    if (bail) { sum = 1.0; j_end = 1; }
-
-    // ---- pass 2: normalise, accumulate states 1 .. j_end-1 ----------------------------
-    // (pass 1 established that states >= j_end contribute nothing)
-    const Recip z = make_recip(sum);
-    const double pn0 = z.yh;  // p[0]/sum = RN(1/sum)
-    double acc = 0.0, sum_p = pn0, pn = 0.0, di = 1.0, acc_at_N = 0.0;
-    bool captured = false;
-    p = p1;
-    __syncwarp(warp_mask);
-#pragma unroll 2
-    for (int i = 1; i < j_end; ++i) {
-        const bool fast = in_window(p, kHiPLo, kHiPHi);
-        if (fast) {
-            pn = div_recip(p, z);
-        } else {
-            if (p == 0.0) { pn = 0.0; break; }
-            pn = __ddiv_rn(p, sum);
-        }
-        acc = __dadd_rn(acc, __dmul_rn(di, pn));
-        di = __dadd_rn(di, 1.0);
-        if (i <= N) {
-            sum_p = __dadd_rn(sum_p, pn);
-            if (i == N) { acc_at_N = acc; captured = true; }  // :50-54
-        }
-        if (i + 1 < j_end) {
-            const double a = __dmul_rn(p, lam);
-            if (fast)
-                p = step_fast<TAB>(tab, stride, i, nh, tail, a);
-            else
-                p = __ddiv_rn(a, step_recip<TAB>(tab, stride, i, nh, tail).b);
-        }
-    }
-    __syncwarp(warp_mask);
-    // when the chain ended before state N the remaining updates of acc and sumP are no-ops
-    if (!captured) acc_at_N = acc;
-    const double in_serv = __dadd_rn(acc_at_N, __dmul_rn(__dsub_rn(1.0, sum_p), (double)N));
-    // p[K]/sum: pn if the chain ran to K, otherwise below 2^-77 (so 1 - float32(.) == 1)
-    const double pnK = (j_end == K + 1) ? pn : 0.0;
-
-    // ---- float32 tail: mm1modelstatedependent.go:56-66 --------------------------
-    st.avg_num_in_servers = (float)in_serv;
-    const float avg_num_in_system = (float)acc;
-    st.throughput = __fmul_rn(lambda, __fsub_rn(1.0f, (float)pnK));
-    st.avg_resp_time = __fdiv_rn(avg_num_in_system, st.throughput);
-    st.avg_serv_time = __fdiv_rn(st.avg_num_in_servers, st.throughput);
-    float w = __fsub_rn(st.avg_resp_time, st.avg_serv_time);
-    if (w < 0.0f) w = 0.0f;
-    st.avg_wait_time = w;
-    return bail ? kSolveBail : kSolveOk;
-}
-
 // ---------------------------------------------------------------------------
-// Shared-table solver (grid and sweep kernels): same arithmetic as solve_model<TAB_SHARED>,
-// restructured for issue efficiency.  The hot loops contain only the recurrence: one merged
+// Shared-table solver (grid, size and sweep kernels), structured for issue efficiency.  The hot loops contain only the recurrence: one merged
 // exponent-window test per step covers "p is negligible / zero / tiny / too large"; the
 // reciprocal triple stays in registers and is re-loaded only while n <= N-1 (table entry
 // N-1 is the tail, so no select between head and tail values is needed); everything rare

@@ -6,8 +6,7 @@
 //                       feasibility + cost + transition penalty + warp-shuffle argmin
 //   grid_fallback       stored-vector re-run of the rare cells the streaming solve bails on
 //   grid_finalize  K3   per-server argmin over partials (warp shuffle -> smem -> record)
-//   build_lane_tables   float32 servRate columns, coalesced per 32-candidate group
-//   size_kernel    K1   one CreateAllocation per (server, acc) candidate (2 bisections)
+//   sz_* kernels   K1   CreateAllocation per (server, acc) candidate as rounds of sorted solve batches
 //   size_fallback       stored-vector re-run of candidates that bailed
 //   trivial_kernel      nil / zero-load candidates
 //   unlimited_kernel    Server.Calculate value + SolveUnlimited argmin per server
@@ -611,37 +610,7 @@ __global__ void __launch_bounds__(128) grid_finalize(GridArgs g, AllocCols winne
 // K1: size candidates (CreateAllocation).
 // ---------------------------------------------------------------------------
 
-// float32 servRate columns: group gidx holds 32 consecutive candidates of the sorted
-// list; element n of lane l at ltab[group_off[gidx] + n*32 + l].
-__global__ void build_lane_tables(DevFleet f, const int* __restrict__ cand_pair, const int* __restrict__ cand_N,
-                                  int n_cand, const long long* __restrict__ group_off, float* __restrict__ ltab) {
-    const int gidx = blockIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int j = gidx * 32 + lane;
-    const bool live = j < n_cand;
-    const int pair = live ? cand_pair[j] : 0;
-    const int N = live ? cand_N[j] : 0;
-    const int Ng = cand_N[gidx * 32];  // sorted descending: the first lane has the largest N
-    QParams q;
-    if (live) q = qparams_of(f, pair / f.A, pair % f.A);
-    float* out = ltab + group_off[gidx];
-    for (int n = threadIdx.x >> 5; n < Ng; n += blockDim.x >> 5) {
-        out[(size_t)n * 32 + lane] = (live && n < N) ? serv_rate(q, n + 1) : 1.0f;
-    }
-}
-
 // Solver policies: a solver evaluates Model.Solve(lambda, 1) and reports bail-outs.
-struct LaneSolver {  // streaming solve on the lane's float32 column
-    const float* col;
-    int N, K, n_mono;
-    Recip tail;
-    int bail;
-    __device__ __forceinline__ int solve(float lambda, ModelStats& st) {
-        const int rc = solve_model<TAB_LANE>(col, 32, n_mono, N, K, lambda, tail, st);
-        if (rc != kSolveOk) bail = 1;
-        return rc;
-    }
-};
 struct StoredSolver {  // stored-vector fallback
     double* p;
     const float* sr;
@@ -764,39 +733,11 @@ struct SizeArgs {
     const int* cand_pair;  // [n_cand] pair ids sorted by descending N
     const int* cand_N;     // [n_cand]
     int n_cand;
-    const float* ltab;
-    const long long* group_off;
     AllocCols cand;        // [S*A]
     int* fb_count;
     int* fb_list;          // candidate indices that bailed
     int fb_cap;
 };
-
-__global__ void __launch_bounds__(128) size_kernel(SizeArgs g) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= g.n_cand) return;
-    const DevFleet& f = g.f;
-    const int pair = g.cand_pair[j];
-    const int s = pair / f.A, a = pair % f.A;
-    LaneSolver sv;
-    sv.N = g.cand_N[j];
-    sv.K = sv.N + sv.N * f.ratio;
-    sv.col = g.ltab + g.group_off[j >> 5] + (j & 31);
-    sv.bail = 0;
-    const float s1 = sv.col[0], sN = sv.col[(size_t)(sv.N - 1) * 32];
-    sv.tail = make_recip((double)sN);
-    sv.n_mono = sv.N - 1;  // index from which the service-rate column is non-decreasing
-    for (int n = sv.N - 2; n >= 0; --n) {
-        if (sv.col[(size_t)n * 32] <= sv.col[(size_t)(n + 1) * 32]) sv.n_mono = n; else break;
-    }
-    Cand c = create_allocation(f, s, a, sv, s1, sN);
-    if (sv.bail) {
-        const int k = atomicAdd(g.fb_count, 1);
-        if (k < g.fb_cap) g.fb_list[k] = j;
-        c = cand_nil();
-    }
-    store_cand(g.cand, pair, c);
-}
 
 // Stored-vector re-run of bailed candidates (slot k handles list entries k, k+n_slots, ..).
 __global__ void size_fallback(SizeArgs g, double* scratch, size_t slot_doubles, int Kmax, int* fb_status) {
