@@ -175,3 +175,15 @@ def test_full_size_properties_config2_slice(engine):
     _, win2 = engine.grid_solve(fleet, grid)
     for k, v in win.columns().items():
         assert np.array_equal(v.view(np.uint8), win2.columns()[k].view(np.uint8))
+
+
+def test_exact_division_primitive_selfcheck(engine):
+    """div_recip (4 dependent FP64 ops around a double-word reciprocal) must equal div.rn.f64 bit for bit
+    on 2 x 10^9 pseudo-random operand pairs from the solver's exponent windows, including float32-valued
+    divisors and divisors next to powers of two."""
+    import ctypes as C
+    L = engine._L
+    L.wva_dbg_div_selfcheck.restype = C.c_longlong
+    L.wva_dbg_div_selfcheck.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int]
+    bad = L.wva_dbg_div_selfcheck(engine._h, 0x5EED, 148 * 16, 1800)   # 148*16*256*1800*2 = 2.2e9 divisions
+    assert bad == 0

@@ -1431,8 +1431,63 @@ int wva_sweep(wva_handle* h, const wva_fleet* fleet, int32_t n_rates, wva_sweep_
     return WVA_OK;
 }
 
+// ---- self-check of the exact-division primitive (not part of the public ABI) ------------------
+// Compares div_recip (Markstein correction around a double-word reciprocal) with div.rn.f64 on
+// pseudo-random operands drawn from the solver's exponent windows, including adversarial
+// divisors next to powers of two and float32-valued divisors.  Returns the mismatch count.
+__global__ void div_selfcheck_kernel(unsigned long long seed, int iters, unsigned long long* mismatches) {
+    unsigned long long x = seed ^ (0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1));
+    auto next = [&]() {  // xorshift64*
+        x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+        return x * 0x2545F4914F6CDD1Dull;
+    };
+    unsigned long long bad = 0;
+    for (int it = 0; it < iters; ++it) {
+        const unsigned long long r0 = next(), r1 = next(), r2 = next();
+        // divisor: mantissa random / float32-valued / all-ones / one-above-power-of-two; exponent in [-60, 60]
+        unsigned long long mb = r0 & 0x000FFFFFFFFFFFFFull;
+        switch (r2 & 3) {
+        case 0: mb &= 0x000FFFFFE0000000ull; break;                 // float32-valued (24-bit significand)
+        case 1: mb = 0x000FFFFFFFFFFFFFull - (r0 & 0xff); break;    // just below a power of two
+        case 2: mb = r0 & 0xff; break;                              // just above a power of two
+        default: break;
+        }
+        const long long eb = (long long)((r2 >> 8) % 121) - 60;
+        const double b = __longlong_as_double((long long)(((unsigned long long)(1023 + eb) << 52) | mb));
+        // dividend: random mantissa (sometimes all ones), exponent in [-340, 660] (p * lambda)
+        unsigned long long ma = r1 & 0x000FFFFFFFFFFFFFull;
+        if (((r2 >> 20) & 7) == 0) ma = 0x000FFFFFFFFFFFFFull - (r1 & 0xf);
+        const long long ea = (long long)((r2 >> 24) % 1001) - 340;
+        const double a = __longlong_as_double((long long)(((unsigned long long)(1023 + ea) << 52) | ma));
+        const Recip rc = make_recip(b);
+        const double q = div_recip(a, rc), want = __ddiv_rn(a, b);
+        if (__double_as_longlong(q) != __double_as_longlong(want)) ++bad;
+        // the cheaper low word used for the normalising sum (zl = RN(e * zh))
+        Recip z = rc;
+        z.yl = __dmul_rn(__fma_rn(-b, rc.yh, 1.0), rc.yh);
+        const double q2 = div_recip(a, z);
+        if (__double_as_longlong(q2) != __double_as_longlong(want)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ---- diagnostics (not part of the public ABI) ------------------------------------------
 // Per-cell SM cycles of the last grid solve, in launch order, followed by the cell ids.
+// Runs blocks*256*iters*2 random divisions; returns the number of results that differ from div.rn.f64.
+long long wva_dbg_div_selfcheck(wva_handle* h, unsigned long long seed, int blocks, int iters) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, sizeof(unsigned long long)) != cudaSuccess) return -1;
+    cudaMemsetAsync(d, 0, sizeof(unsigned long long), h->stream);
+    div_selfcheck_kernel<<<blocks, 256, 0, h->stream>>>(seed, iters, d);
+    unsigned long long out = ~0ull;
+    cudaMemcpyAsync(&out, d, sizeof(out), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    return (long long)out;
+}
+
 int wva_dbg_enable_cycles(wva_handle* h, int on) {
     if (!h) return WVA_ERR_BAD_ARG;
     h->dbg_cycles = on != 0;

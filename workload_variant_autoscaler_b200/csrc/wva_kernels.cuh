@@ -336,7 +336,7 @@ __device__ __forceinline__ void decode_cell(const GridArgs& g, long long cell, i
 
 // Estimated number of chain states before exact early termination (scheduling only; any
 // value is correct, a good one makes the 32 lanes of a warp finish together).
-__device__ __forceinline__ float estimate_len(const double* tab, const float* ls, int N, int K, float lambda,
+__device__ __forceinline__ float estimate_len(const double* /*tab*/, const float* ls, int N, int K, float /*lambda*/,
                                               float l2lam, float l2s0, float l2sN, float lsNm1) {
     const float thr = -78.0f + fminf(0.0f, l2lam - l2s0);
     const float d = l2sN - l2lam;                     // tail decay per state (> 0 when analysable)
@@ -345,15 +345,10 @@ __device__ __forceinline__ float estimate_len(const double* tab, const float* ls
     if (L0 >= thr || N == 1) {
         est = (float)(N - 1) + (L0 - thr) / fmaxf(d, 1e-9f) + 2.0f;
     } else {
-        // the chain dies inside the head: first j past the mode with log2 p[j] < thr
-        const unsigned hl = (unsigned)__double2hiint((double)lambda);
-        int lo = 1, hi = N - 1;  // smallest j with lambda < min(servRate[j..])
+        // the chain dies inside the head.  log2 p[j] = j*l2lam - ls[j] rises from 0 to the mode and
+        // falls afterwards, and thr < 0, so {j : log2 p[j] < thr} is an upper set: one binary search
+        int lo = 1, hi = N - 1;
         while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (hl < (unsigned)__double2hiint(tab[4 * mid + 3])) hi = mid; else lo = mid + 1;
-        }
-        hi = N - 1;
-        while (lo < hi) {  // log2 p[j] = j*l2lam - ls[j] is decreasing past the mode
             const int mid = (lo + hi) >> 1;
             if ((float)mid * l2lam - ls[mid] < thr) hi = mid; else lo = mid + 1;
         }
@@ -378,6 +373,26 @@ __device__ __forceinline__ unsigned agg_inc(unsigned* counters, int key) {
     return base + __popc(peers & ((1u << lane) - 1u));
 }
 
+// Counter increment for lanes whose equal keys sit in CONTIGUOUS lane ranges (along a row the
+// length class is monotone in the replica level, so equal classes are adjacent): one atomic per
+// run instead of one per lane, found with a shuffle and a ballot.  Returns the lane's slot.
+__device__ __forceinline__ unsigned seg_inc(unsigned* counters, int key) {
+    const unsigned act = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int prev = __shfl_up_sync(act, key, 1);
+    const bool prev_active = lane > 0 && ((act >> (lane - 1)) & 1u);
+    const unsigned heads = __ballot_sync(act, !prev_active || prev != key);
+    const unsigned upto = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
+    const int seg_start = 31 - __clz(heads & upto);
+    const unsigned above = heads & ~upto;
+    const int seg_end = above ? (__ffs(above) - 1) : 32;  // exclusive; inactive lanes start a new run too
+    const unsigned seg_mask = (seg_end == 32 ? 0xffffffffu : ((1u << seg_end) - 1u)) & ~((1u << seg_start) - 1u) & act;
+    unsigned base = 0;
+    if (lane == seg_start) base = atomicAdd(&counters[key], (unsigned)__popc(seg_mask));
+    base = __shfl_sync(act, base, seg_start);
+    return base + __popc(seg_mask & ((1u << lane) - 1u));
+}
+
 // Estimate + LOCAL counting sort, one CTA per chunk of kSortChunk consecutive cells (cells of
 // one or two (server, accelerator) pairs): length classes are computed into shared memory,
 // histogrammed, scanned and scattered without leaving the CTA.  Each run of 32 sorted cells
@@ -394,24 +409,39 @@ __global__ void __launch_bounds__(kSortThreads) grid_sort_local(GridArgs g) {
     __syncthreads();
     const long long base = (long long)blockIdx.x * kSortChunk;
     const int n_here = (int)min((long long)kSortChunk, g.n_cells - base);
-    for (int k = threadIdx.x; k < n_here; k += kSortThreads) {
-        const long long cell = base + k;
-        int s, a, bi, ri;
-        decode_cell(g, cell, s, a, bi, ri);
-        int key = 255;
-        const long long toff = g.pair_tab_off[s * f.A + a];
-        if (toff >= 0) {
+    // walk the chunk row by row (a row = the R replica levels of one (server, accelerator, batch)):
+    // the row's constants are decoded once per warp, lanes take the replica levels
+    {
+        const unsigned R = (unsigned)g.R, B = (unsigned)g.B, A = (unsigned)f.A;
+        const unsigned row0 = (unsigned)(base / R), row1 = (unsigned)((base + n_here - 1) / R);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (unsigned row = row0 + warp; row <= row1; row += kSortThreads / 32) {
+            const unsigned sa = row / B;
+            const int bi = (int)(row - sa * B);
+            const int s = (int)(sa / A);
+            const long long toff = g.pair_tab_off[sa];
             const int b = g.batch[bi];
             const int K = b + b * f.ratio;
-            const int t = g.pair_tab_idx[s * f.A + a];
-            const float4 pb = g.pb[(size_t)t * g.B + bi];
-            const float4 rt = g.rt[s * g.R + ri];
-            if (!(rt.x <= 0.0f) && !(rt.x > pb.x) && K >= 2) {  // Analyze: queueanalyzer.go:135-143
-                key = length_class(estimate_len(g.tab + 4 * toff, g.ls + toff + t, b, K, rt.y, rt.z, pb.w, pb.y, pb.z));
+            int t = 0;
+            float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (toff >= 0) {
+                t = g.pair_tab_idx[sa];
+                pb = g.pb[(size_t)t * g.B + bi];
+            }
+            for (unsigned ri = lane; ri < R; ri += 32) {
+                const long long cell = (long long)row * R + ri;
+                if (cell < base || cell >= base + n_here) continue;
+                int key = 255;
+                if (toff >= 0) {
+                    const float4 rt = g.rt[(unsigned)s * R + ri];
+                    if (!(rt.x <= 0.0f) && !(rt.x > pb.x) && K >= 2) {  // Analyze: queueanalyzer.go:135-143
+                        key = length_class(estimate_len(g.tab + 4 * toff, g.ls + toff + t, b, K, rt.y, rt.z, pb.w, pb.y, pb.z));
+                    }
+                }
+                keys[cell - base] = (uint8_t)key;
+                seg_inc(hist, key);
             }
         }
-        keys[k] = (uint8_t)key;
-        agg_inc(hist, key);
     }
     __syncthreads();
     if (threadIdx.x < 32) {  // exclusive scan of the 256 class counts by one warp
@@ -432,7 +462,7 @@ __global__ void __launch_bounds__(kSortThreads) grid_sort_local(GridArgs g) {
     const int n_active = (int)cursor[255];  // class 255 (not analysable) sorts last
     for (int k = threadIdx.x; k < n_here; k += kSortThreads) {
         const int key = keys[k];
-        const unsigned pos = agg_inc(cursor, key);
+        const unsigned pos = seg_inc(cursor, key);
         g.order[base + pos] = (unsigned)(base + k);
         sorted_keys[pos] = (uint8_t)key;
     }
