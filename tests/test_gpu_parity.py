@@ -187,3 +187,98 @@ def test_exact_division_primitive_selfcheck(engine):
     L.wva_dbg_div_selfcheck.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int]
     bad = L.wva_dbg_div_selfcheck(engine._h, 0x5EED, 148 * 16, 1800)   # 148*16*256*1800*2 = 2.2e9 divisions
     assert bad == 0
+
+
+def test_config2_full_resolution_sample_bit_exact(engine, oracle_mod):
+    """BASELINE configs[1] at full batch x replica resolution (256 x 64): five of the 100 models are
+    checked cell-by-cell and winner-by-winner against the oracle (1.3 M cells)."""
+    from workload_variant_autoscaler_b200 import config2_grid
+    full = synth_fleet(100, 4, seed=42)
+    grid = config2_grid()
+    idx = np.array([0, 23, 47, 71, 99])
+    sub = full.take_servers(idx)
+    cells_o, win_o = oracle_mod.grid_solve(sub, grid, want_cells=True)
+    # the sampled servers solved alone ...
+    cells_g, win_g = engine.grid_solve(sub, grid, want_cells=True)
+    assert np.array_equal(cells_g["flags"], cells_o["flags"])
+    for k in ("ttft", "itl", "rho", "throughput"):
+        assert_f32_bits_equal(cells_g[k], cells_o[k], f"cells.{k}")
+    assert_allocs_equal(win_g, win_o, "winners of the sampled models")
+    # ... and inside the full 100-model solve (scheduling differs, results must not)
+    _, win_full = engine.grid_solve(full, grid)
+    for name in ("feasible", "acc", "replicas", "batch"):
+        assert np.array_equal(np.asarray(getattr(win_full, name))[idx].astype(np.int64), win_o[name].astype(np.int64)), name
+    for name in ("cost", "value", "itl", "ttft", "rho", "max_rate"):
+        assert_f32_bits_equal(getattr(win_full, name)[idx], win_o[name], f"full-solve winners {name}")
+
+
+def test_empty_and_degenerate_fleets(engine, oracle_mod):
+    f0 = synth_fleet(4, 2, seed=1).take_servers(np.array([], dtype=np.int64))   # no servers
+    cand, win = engine.solve(f0)
+    assert cand.n == 0 and win.n == 0
+    _, gw = engine.grid_solve(f0, Grid([1, 2], [1, 2]))
+    assert gw.n == 0
+    f1 = synth_fleet(3, 2, seed=2)
+    f1.perf_present[:] = 0                                                        # nothing analysable
+    cand, win = engine.solve(f1)
+    assert cand.feasible.sum() == 0 and win.feasible.sum() == 0
+    cells, gw = engine.grid_solve(f1, Grid([1, 4], [1, 2, 3]), want_cells=True)
+    assert cells["flags"].sum() == 0 and gw.feasible.sum() == 0
+    f2 = synth_fleet(5, 2, seed=3, max_batch_choices=(1,))                        # N = 1 everywhere (K = 11)
+    _grid_check(engine, oracle_mod, f2, Grid([1], [1, 2, 50]))
+    cand_o, win_o = oracle_mod.solve(f2)
+    cand_g, win_g = engine.solve(f2)
+    assert_allocs_equal(cand_g, cand_o, "N = 1 candidates")
+    f3 = synth_fleet(5, 2, seed=4)
+    f3.max_queue_to_batch_ratio = 0                                               # K = N: N = 1 is never valid
+    _grid_check(engine, oracle_mod, f3, Grid([1, 2, 8], [1, 4]))
+    f3.max_queue_to_batch_ratio = 3
+    f3.accel_penalty_factor = 0.25
+    _grid_check(engine, oracle_mod, f3, Grid([1, 2, 8], [1, 4]))
+    cand_o, win_o = oracle_mod.solve(f3)
+    cand_g, win_g = engine.solve(f3)
+    assert_allocs_equal(win_g, win_o, "non-default tunables")
+
+
+def test_abi_error_paths(engine):
+    import ctypes as C
+    from workload_variant_autoscaler_b200 import WvaError, _abi
+    L = engine._L
+    f = synth_fleet(3, 2, seed=5)
+    win = _abi.Allocs(3).as_c()
+    assert L.wva_solve(engine._h, None, None, C.byref(win)) == _abi.WVA_ERR_BAD_ARG          # NULL fleet
+    fc = f.as_c()
+    fc.srv_model = None
+    assert L.wva_solve(engine._h, C.byref(fc), None, C.byref(win)) == _abi.WVA_ERR_BAD_ARG   # NULL column
+    fc = f.as_c()
+    fc.n_servers = -1
+    assert L.wva_solve(engine._h, C.byref(fc), None, C.byref(win)) == _abi.WVA_ERR_BAD_ARG   # negative size
+    with pytest.raises(WvaError):
+        engine.grid_solve(f, Grid([0, 2], [1]))                                              # batch < 1
+    with pytest.raises(WvaError):
+        engine.grid_solve(f, Grid([2], [0]))                                                 # replicas < 1
+    h2 = C.c_void_p()
+    assert L.wva_create(C.byref(h2), 0) == 0
+    assert L.wva_resolve(h2, None, C.byref(win)) == _abi.WVA_ERR_STATE                       # resolve before upload
+    assert b"upload" in L.wva_last_error(h2)
+    L.wva_destroy(h2)
+    assert L.wva_create(C.byref(h2), 4096) == _abi.WVA_ERR_NO_DEVICE                        # no such device
+    # infeasibility is data, not an error
+    f.srv_has_target[:] = 0
+    _, w = engine.solve(f)
+    assert w.feasible.sum() == 0
+
+
+def test_ties_resolve_to_lowest_accelerator(engine, oracle_mod):
+    f = synth_fleet(6, 3, seed=6, max_batch_choices=(8,))
+    for col in ("perf_alpha", "perf_beta", "perf_gamma", "perf_delta", "perf_acc_count"):
+        getattr(f, col)[:, 1] = getattr(f, col)[:, 0]
+        getattr(f, col)[:, 2] = getattr(f, col)[:, 0]
+    f.acc_cost[:] = 40.0
+    f.srv_cur_acc[:] = -1
+    f.srv_cur_replicas[:] = 0
+    f.srv_cur_cost[:] = 0
+    cand_o, win_o = oracle_mod.solve(f)
+    _, win_g = engine.solve(f)
+    assert_allocs_equal(win_g, win_o, "tie winners")
+    assert (np.asarray(win_g.acc)[np.asarray(win_g.feasible) == 1] == 0).all()
