@@ -1,4 +1,4 @@
-"""Diagnostics: per-cell SM cycles of grid_kernel on BASELINE config 2 (run on the GPU box)."""
+"""Diagnostics: per-lane SM cycles of grid_kernel on BASELINE config 2 (run on the GPU box)."""
 import ctypes as C
 import sys
 
@@ -15,22 +15,21 @@ L.wva_dbg_enable_cycles(e._h, 1)
 e.grid_solve(f, g)
 e.grid_solve(f, g)
 n = f.n_servers * f.n_acc * 256 * 64
-cyc = np.zeros(n, np.uint32)
-cells = np.zeros(n, np.uint32)
+cyc = np.zeros(2 * n, np.uint32)
+cells = np.zeros(2 * n, np.uint32)
 L.wva_dbg_read_cycles.restype = C.c_longlong
 got = L.wva_dbg_read_cycles(e._h, cyc.ctypes.data_as(C.c_void_p), cells.ctypes.data_as(C.c_void_p), C.c_longlong(n))
-print("cells", got, "kernel ms", e.last_kernel_ms)
+print("kernel ms", e.last_kernel_ms)
 cyc = cyc[:got]
-print("sum cycles %.3e  mean %.1f  max %d" % (cyc.sum(dtype=np.float64), cyc.mean(), cyc.max()))
-w = cyc.reshape(-1, 32) if got % 32 == 0 else cyc[: got // 32 * 32].reshape(-1, 32)
-wmax = w.max(axis=1)
-print("warp-max sum %.3e (x32 = %.3e lane-cycles)" % (wmax.sum(dtype=np.float64), 32.0 * wmax.sum(dtype=np.float64)))
-for q in (50, 90, 99, 99.9, 100):
-    print("pct", q, np.percentile(cyc, q))
-top = np.argsort(-cyc.astype(np.int64))[:10]
-for i in top:
-    c = int(cells[i]); ri = c % 64; bi = (c // 64) % 256; a = (c // (64 * 256)) % 4; s = c // (64 * 256 * 4)
-    print("idx", i, "cycles", cyc[i], "cell s,a,b,r", s, a, bi + 1, ri + 1)
-blk = cyc[: got // 256 * 256].reshape(-1, 256).max(axis=1)
-print("block max: first 10", blk[:10], " mean", blk.mean(), "max", blk.max(), "argmax", blk.argmax(), "of", blk.size)
-print("blocks with max > 1e6 cycles:", (blk > 1e6).sum(), " > 1e5:", (blk > 1e5).sum())
+w = cyc[: got // 32 * 32].reshape(-1, 32).max(axis=1)
+w = w[w > 0]
+print("warps with work", w.size, "sum warp cycles %.3e" % w.sum(dtype=np.float64), "mean", w.mean(), "max", w.max())
+for q in (10, 50, 90, 99, 99.9):
+    print("pct", q, np.percentile(w, q))
+print("first 20 warps (launch order):", w[:20])
+order = np.sort(w)[::-1]
+cs = np.cumsum(order, dtype=np.float64)
+for frac in (0.01, 0.05, 0.1, 0.25, 0.5):
+    k = int(frac * w.size)
+    print("top %4.0f%% of warps hold %5.1f%% of warp-cycles" % (100 * frac, 100 * cs[k] / cs[-1]))
+print("ideal ms if perfectly packed on 148 SMs x 32 warps:", w.sum(dtype=np.float64) / (148 * 32) / 1.965e9 * 1e3)

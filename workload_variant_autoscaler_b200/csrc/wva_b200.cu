@@ -141,7 +141,7 @@ struct wva_handle {
     uint64_t grid_epoch = ~0ull;
     std::vector<int> grid_batch, grid_replicas;
     int grid_Bmax = 0, grid_n_tab = 0;
-    DevBuf d_grid_lists, d_pair_tab, d_tab_pair, d_tab_off, d_tab_len, d_tab, d_ls, d_sort, d_best, d_pb;
+    DevBuf d_grid_lists, d_pair_tab, d_tab_pair, d_tab_off, d_tab_len, d_tab, d_ls, d_sort, d_best, d_pb, d_rows;
     // shared
     DevBuf d_cand_block, d_win_block, d_ctrl, d_fb_list, d_scratch, d_cells, d_sweep, d_dbg;
     bool dbg_cycles = false;
@@ -766,6 +766,11 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     const size_t n_best = std::max<size_t>((size_t)S * A * R, 1);
     CK(h->d_best.ensure(sizeof(int) * n_best));
     g.best_rank = (int*)h->d_best.p;
+    CK(h->d_rows.ensure((2 * sizeof(double) + sizeof(int)) * n_best + 64));
+    g.row_acc = (double*)h->d_rows.p;
+    g.row_sump = g.row_acc + n_best;
+    g.row_j = (int*)(g.row_sump + n_best);
+    g.Bmax = h->grid_Bmax;
     g.fb_count = (int*)h->d_ctrl.p + CTRL_FB_COUNT;
     g.fb_cap = (int)std::min<size_t>(nc, (size_t)1 << 22);
     CK(h->d_fb_list.ensure(sizeof(long long) * g.fb_cap));
@@ -793,6 +798,8 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
         CK(cudaMemsetAsync(g.cells.flags, 0, plan.n_cells, h->stream));
         fill_int<<<(unsigned)((n_best + 255) / 256), 256, 0, h->stream>>>(g.best_rank, n_best, INT_MAX);
         CK(cudaMemsetAsync(g.item_count, 0, sizeof(unsigned) * (2 * kClasses + 1), h->stream));
+        grid_rows<<<(unsigned)((n_best + 127) / 128), 128, 0, h->stream>>>(g);
+        h->launches++;
         grid_sort_local<<<plan.n_blocks, kSortThreads, 0, h->stream>>>(g);
         // one warp per item; the item count lives on the device, so launch for the worst case
         const size_t max_items = (plan.n_cells + 31) / 32 + (size_t)plan.n_blocks;
@@ -801,7 +808,12 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
         h->launches++;
         const unsigned blocks = (unsigned)((max_items * 32 + 255) / 256);
         CK(cudaEventRecord(h->ev_k0, h->stream));  // wva_last_kernel_ms = the dominant kernel alone
-        grid_kernel<<<blocks, 256, 8 * kGridStash * 32 * sizeof(double), h->stream>>>(g);
+        size_t smem = 8 * kGridStash * 32 * sizeof(double);
+        if (const char* e = getenv("WVA_GRID_SMEM_KB")) {  // experiment: cap the resident blocks per SM
+            smem = std::max<size_t>(smem, (size_t)atoi(e) * 1024);
+            cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        grid_kernel<<<blocks, 256, smem, h->stream>>>(g);
         h->launches += 4;
     }
     CK(cudaEventRecord(h->ev_k1, h->stream));
@@ -1143,7 +1155,7 @@ void wva_destroy(wva_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->arena, &h->d_cand_pair, &h->d_cand_N, &h->d_sz_tab, &h->d_sz_ls, &h->d_sz_off, &h->d_sz_state, &h->d_sz_req, &h->d_sz_sort, &h->d_grid_lists,
-                      &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_ls, &h->d_sort, &h->d_best, &h->d_pb,
+                      &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_ls, &h->d_sort, &h->d_best, &h->d_pb, &h->d_rows,
                       &h->d_cand_block, &h->d_win_block, &h->d_ctrl, &h->d_fb_list, &h->d_scratch,
                       &h->d_cells, &h->d_sweep};
     for (DevBuf* b : bufs) b->release();

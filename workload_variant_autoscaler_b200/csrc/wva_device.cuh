@@ -167,7 +167,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // STASH > 0: the first STASH states of pass 1 are kept in shared memory (stash[(j-1)*32] for
 // state j, one 8-byte column per lane) and pass 2 reads them back instead of re-running the
 // recurrence for those states — most grid chains are shorter than that.
-template <int STASH>
+template <int STASH, int PF = 10>
 __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st,
                                            double* __restrict__ stash) {
     const unsigned warp_mask = __activemask();
@@ -203,7 +203,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             for (;;) {
                 if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) break;
                 if (n < nh) {  // triple of step n+2 (B already holds n+1); prefetch two lines ahead
-                    prefetch_l1(tab + 4 * (n + 10));
+                    prefetch_l1(tab + 4 * (n + PF));
                 }
                 p = div_recip(__dmul_rn(p, lam), A);
                 if (n < nh) load_recip(tab, n + 2 < nh ? n + 2 : nh, A);
@@ -281,7 +281,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
             for (;;) {
                 if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
-                if (i < nh) prefetch_l1(tab + 4 * (i + 10));
+                if (i < nh) prefetch_l1(tab + 4 * (i + PF));
                 pn = div_recip(p, z);
                 const double a0 = __dmul_rn(p, lam);
                 acc = __dadd_rn(acc, __dmul_rn(di, pn));
@@ -337,8 +337,87 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     return bail ? kSolveBail : kSolveOk;
 }
 
+// ---------------------------------------------------------------------------
+// Row solve (grid): the chain of a (server, accelerator, replica level) triple with an
+// "infinitely large" batch, i.e. running on the head of the table only.  If that chain ends
+// (early termination or underflow to 0) at state j_last, then for EVERY batch size b >= j_last + 2
+// the cell's own chain is this very chain: it reads the same rates servRate[0..j_last-1], takes the
+// same head-type exit test at the same state, never reaches its tail, and every state it
+// accumulates lies below N = b.  Those cells therefore share pass 1 and pass 2 outright (same
+// operations in the same order, hence the same bits) and differ only in the N-dependent float
+// tail, which grid_sort_local evaluates per cell.  Anything off the plain fast path (tiny p that
+// needs IEEE division, a chain that reaches the table end, window violations) just reports
+// "no sharing" and the cells go through grid_kernel as usual.
+// ---------------------------------------------------------------------------
+__device__ __noinline__ bool solve_row(const double* __restrict__ tab, int len, float lambda, double& acc_out,
+                                       double& sump_out, int& j_last) {
+    const double lam = (double)lambda;
+    const int nh = len - 1;
+    Recip A;
+    load_recip(tab, 0, A);
+    if (!in_window(lam, kHiRateLo, kHiRateHi) || !in_window(A.b, kHiRateLo, kHiRateHi) || nh < 2) return false;
+    double p = div_recip(lam, A);
+    if (!(p >= 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) return false;
+    const double p1 = p;
+    const unsigned thr_hi = (unsigned)__double2hiint(__dmul_rn(fmin(1.0, p1), 0x1p-78));
+    const unsigned lo_eff = thr_hi > kHiPLo ? thr_hi : kHiPLo;
+    const unsigned span_eff = kHiPHi - lo_eff;
+    double sum = __dadd_rn(1.0, p);
+    int n = 1;
+    while (n < nh && WVA_FASTWIN(p, lo_eff, span_eff)) {
+        load_recip(tab, n, A);
+        p = div_recip(__dmul_rn(p, lam), A);
+        sum = __dadd_rn(sum, p);
+        ++n;
+    }
+    if (n >= nh) return false;  // still alive at the end of the table
+    const unsigned hp = (unsigned)__double2hiint(p);
+    const bool negligible = hp < thr_hi && (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tab[4 * n + 3]);
+    if (!negligible && !(p == 0.0)) return false;
+    if (!in_window(sum, kHiSumLo, kHiSumHi)) return false;
+    j_last = n;
+    Recip z;
+    z.b = sum;
+    z.yh = __ddiv_rn(1.0, sum);
+    z.yl = __dmul_rn(__fma_rn(-sum, z.yh, 1.0), z.yh);
+    double acc = 0.0, sum_p = z.yh, di = 1.0;
+    p = p1;
+    for (int i = 1; i <= j_last; ++i) {
+        if (!WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) {
+            if (p == 0.0) break;  // adds nothing (the cell's pass 2 stops here as well)
+            return false;
+        }
+        const double pn = div_recip(p, z);
+        acc = __dadd_rn(acc, __dmul_rn(di, pn));
+        di = __dadd_rn(di, 1.0);
+        sum_p = __dadd_rn(sum_p, pn);
+        load_recip(tab, i, A);
+        p = div_recip(__dmul_rn(p, lam), A);
+    }
+    acc_out = acc;
+    sump_out = sum_p;
+    return true;
+}
+// Model statistics of a cell that shares its row's chain: mm1modelstatedependent.go:50-66 with
+// avgNumInSystem = acc, sumP complete at i == N, p[K] negligible.
+__device__ __forceinline__ void stats_from_row(double acc, double sum_p, int N, float lambda, ModelStats& st) {
+    const double in_serv = __dadd_rn(acc, __dmul_rn(__dsub_rn(1.0, sum_p), (double)N));
+    st.avg_num_in_servers = (float)in_serv;
+    const float avg_num_in_system = (float)acc;
+    st.throughput = __fmul_rn(lambda, __fsub_rn(1.0f, 0.0f));
+    st.avg_resp_time = __fdiv_rn(avg_num_in_system, st.throughput);
+    st.avg_serv_time = __fdiv_rn(st.avg_num_in_servers, st.throughput);
+    float w = __fsub_rn(st.avg_resp_time, st.avg_serv_time);
+    if (w < 0.0f) w = 0.0f;
+    st.avg_wait_time = w;
+}
+
 __device__ __forceinline__ int solve_shared(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st) {
     return solve_shared_t<0>(tab, N, K, lambda, st, nullptr);
+}
+// Per-lane private tables (size path): every lane streams its own table, so prefetch much further ahead.
+__device__ __forceinline__ int solve_private(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st) {
+    return solve_shared_t<0, 48>(tab, N, K, lambda, st, nullptr);
 }
 
 // Stored-vector fallback: a literal restatement of computeProbabilities /

@@ -307,6 +307,10 @@ struct GridArgs {
     const int* pair_tab_idx;        // [S*A] table index (for the ls / pb columns)
     const float4* pb;               // [n_tab * B] per (table, batch): rmax, log2 sN, ls[N-1], log2 s0
     const float4* rt;               // [S * R] per (server, replica): rate, lambda, log2 lambda
+    double* row_acc;                // [S*A*R] shared-chain results per (server, accelerator, replica)
+    double* row_sump;
+    int* row_j;                     // last state of the shared chain (INT_MAX: no sharing)
+    int Bmax;                       // table length
     long long n_cells;
     unsigned* order;         // [n_cells] cell ids, sorted by length class inside each chunk of kSortChunk cells
     unsigned long long* items;         // warp work items (start | count << 32 | class << 40), unsorted
@@ -373,6 +377,45 @@ __device__ __forceinline__ unsigned agg_inc(unsigned* counters, int key) {
     return base + __popc(peers & ((1u << lane) - 1u));
 }
 
+// SLO feasibility of an analysed cell (the build's grid semantics, SURVEY.md §8d)
+__device__ __forceinline__ bool cell_feasible(const DevFleet& f, int s, int r, float rate, float rmax, const Metrics& m) {
+    const float slo_ttft = f.srv_slo_ttft[s], slo_itl = f.srv_slo_itl[s];
+    bool feas = (slo_ttft == 0.0f || m.ttft <= slo_ttft) && (slo_itl == 0.0f || m.avg_token_time <= slo_itl) &&
+                (r >= f.srv_min_replicas[s]);
+    if (f.srv_slo_tps[s] > 0.0f) {  // Size's stability margin (queueanalyzer.go:231-234)
+        const float lim = __fmul_rn(__fdiv_rn(rmax, 1000.0f), __fsub_rn(1.0f, 0.1f));
+        feas = feas && (__fdiv_rn(rate, 1000.0f) <= lim);
+    }
+    return feas;
+}
+__device__ __forceinline__ void store_cell(const GridArgs& g, long long cell, int ok, int feas, const Metrics& m) {
+    g.cells.flags[cell] = (uint8_t)(ok | (feas << 1));
+    g.cells.ttft[cell] = m.ttft;
+    g.cells.itl[cell] = m.avg_token_time;
+    g.cells.rho[cell] = m.rho;
+    if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
+}
+
+// One lane per (server, accelerator, replica level): the chain every large-enough batch size shares.
+__global__ void __launch_bounds__(128) grid_rows(GridArgs g) {
+    const DevFleet& f = g.f;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= f.S * f.A * g.R) return;
+    const int sa = row / g.R, ri = row - sa * g.R;
+    const int s = sa / f.A;
+    int j = INT_MAX;
+    double acc = 0.0, sump = 0.0;
+    const long long toff = g.pair_tab_off[sa];
+    const float4 rt = g.rt[s * g.R + ri];
+    if (toff >= 0 && rt.x > 0.0f) {
+        int jl = 0;
+        if (solve_row(g.tab + 4 * toff, g.Bmax, rt.y, acc, sump, jl)) j = jl;
+    }
+    g.row_j[row] = j;
+    g.row_acc[row] = acc;
+    g.row_sump[row] = sump;
+}
+
 // Counter increment for lanes whose equal keys sit in CONTIGUOUS lane ranges (along a row the
 // length class is monotone in the replica level, so equal classes are adjacent): one atomic per
 // run instead of one per lane, found with a shuffle and a ballot.  Returns the lane's slot.
@@ -398,7 +441,7 @@ __device__ __forceinline__ unsigned seg_inc(unsigned* counters, int key) {
 // histogrammed, scanned and scattered without leaving the CTA.  Each run of 32 sorted cells
 // becomes one warp work item tagged with its (longest) class; grid_sort_items then orders the
 // items globally, so the launch is longest-first while a pair's cells stay adjacent.
-__global__ void __launch_bounds__(kSortThreads) grid_sort_local(GridArgs g) {
+__global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
     __shared__ uint8_t keys[kSortChunk];
     __shared__ uint8_t sorted_keys[kSortChunk];
     __shared__ unsigned hist[kClasses];
@@ -424,9 +467,11 @@ __global__ void __launch_bounds__(kSortThreads) grid_sort_local(GridArgs g) {
             const int K = b + b * f.ratio;
             int t = 0;
             float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+            QParams q{};
             if (toff >= 0) {
                 t = g.pair_tab_idx[sa];
                 pb = g.pb[(size_t)t * g.B + bi];
+                q = qparams_of(f, s, (int)(sa - (unsigned)s * A));
             }
             for (unsigned ri = lane; ri < R; ri += 32) {
                 const long long cell = (long long)row * R + ri;
@@ -435,7 +480,19 @@ __global__ void __launch_bounds__(kSortThreads) grid_sort_local(GridArgs g) {
                 if (toff >= 0) {
                     const float4 rt = g.rt[(unsigned)s * R + ri];
                     if (!(rt.x <= 0.0f) && !(rt.x > pb.x) && K >= 2) {  // Analyze: queueanalyzer.go:135-143
-                        key = length_class(estimate_len(g.tab + 4 * toff, g.ls + toff + t, b, K, rt.y, rt.z, pb.w, pb.y, pb.z));
+                        const size_t rowid = (size_t)sa * R + ri;
+                        const int jl = g.row_j[rowid];
+                        if (jl != INT_MAX && b >= jl + 2 && K < (1 << 23)) {
+                            // the whole solve is shared with the row: only the N-dependent tail is per cell
+                            ModelStats st;
+                            stats_from_row(g.row_acc[rowid], g.row_sump[rowid], b, rt.y, st);
+                            const Metrics m = metrics_from(q, b, st);
+                            const bool feas = cell_feasible(f, s, g.replicas[ri], rt.x, pb.x, m);
+                            store_cell(g, cell, 1, feas ? 1 : 0, m);
+                            if (feas) atomicMin(&g.best_rank[rowid], g.batch_rank[bi]);
+                        } else {
+                            key = length_class(estimate_len(g.tab + 4 * toff, g.ls + toff + t, b, K, rt.y, rt.z, pb.w, pb.y, pb.z));
+                        }
                     }
                 }
                 keys[cell - base] = (uint8_t)key;
@@ -499,25 +556,6 @@ __global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
     if (i >= n) return;
     const unsigned long long it = g.items[i];
     g.items_sorted[agg_inc(g.item_count + 1 + kClasses, (int)((it >> 40) & 0xff))] = it;
-}
-
-// SLO feasibility of an analysed cell (the build's grid semantics, SURVEY.md §8d)
-__device__ __forceinline__ bool cell_feasible(const DevFleet& f, int s, int r, float rate, float rmax, const Metrics& m) {
-    const float slo_ttft = f.srv_slo_ttft[s], slo_itl = f.srv_slo_itl[s];
-    bool feas = (slo_ttft == 0.0f || m.ttft <= slo_ttft) && (slo_itl == 0.0f || m.avg_token_time <= slo_itl) &&
-                (r >= f.srv_min_replicas[s]);
-    if (f.srv_slo_tps[s] > 0.0f) {  // Size's stability margin (queueanalyzer.go:231-234)
-        const float lim = __fmul_rn(__fdiv_rn(rmax, 1000.0f), __fsub_rn(1.0f, 0.1f));
-        feas = feas && (__fdiv_rn(rate, 1000.0f) <= lim);
-    }
-    return feas;
-}
-__device__ __forceinline__ void store_cell(const GridArgs& g, long long cell, int ok, int feas, const Metrics& m) {
-    g.cells.flags[cell] = (uint8_t)(ok | (feas << 1));
-    g.cells.ttft[cell] = m.ttft;
-    g.cells.itl[cell] = m.avg_token_time;
-    g.cells.rho[cell] = m.rho;
-    if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
 }
 
 __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
@@ -1114,7 +1152,7 @@ __global__ void __launch_bounds__(256) sz_solve(SzArgs g) {
     const int N = g.cand_N[j], K = N + N * f.ratio;
     const float lambda = g.req_lam[slot];
     ModelStats st;
-    const int rc = solve_shared(g.tab + 4 * g.tab_off[j], N, K, lambda, st);
+    const int rc = solve_private(g.tab + 4 * g.tab_off[j], N, K, lambda, st);
     g.req_bail[slot] = rc != kSolveOk;
     if (rc != kSolveOk) return;
     const QParams q = qparams_of(f, pair / f.A, pair % f.A);
