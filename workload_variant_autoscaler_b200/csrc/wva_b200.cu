@@ -798,7 +798,11 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
         CK(cudaMemsetAsync(g.cells.flags, 0, plan.n_cells, h->stream));
         fill_int<<<(unsigned)((n_best + 255) / 256), 256, 0, h->stream>>>(g.best_rank, n_best, INT_MAX);
         CK(cudaMemsetAsync(g.item_count, 0, sizeof(unsigned) * (2 * kClasses + 1), h->stream));
-        grid_rows<<<(unsigned)((n_best + 127) / 128), 128, 0, h->stream>>>(g);
+        {
+            const int rows_threads = g.R >= 128 ? 128 : (g.R > 32 ? 64 : 32);
+            const size_t rows_smem = g.Bmax <= kRowsSmemEntries ? (size_t)g.Bmax * 32 : 0;
+            grid_rows<<<(unsigned)(hf.S * hf.A), rows_threads, rows_smem, h->stream>>>(g);
+        }
         h->launches++;
         grid_sort_local<<<plan.n_blocks, kSortThreads, 0, h->stream>>>(g);
         // one warp per item; the item count lives on the device, so launch for the worst case

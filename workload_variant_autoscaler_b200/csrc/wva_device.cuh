@@ -159,6 +159,14 @@ __device__ __forceinline__ void load_recip(const double* __restrict__ tab, int n
     r.yl = tab[4 * n + 2];
 }
 
+// Table column 4 holds two float32 values: [0] min(servRate[n..]) (suffix minimum; 0 if any rate is NaN),
+// [1] max(servRate[0..n]) (prefix maximum).  Both are exact (the rates are float32 values).
+__device__ __forceinline__ float tab_suffix_min(const double* tab, int n) { return ((const float*)(tab + 4 * n + 3))[0]; }
+__device__ __forceinline__ float tab_prefix_max(const double* tab, int n) { return ((const float*)(tab + 4 * n + 3))[1]; }
+// lambda clearly below m (16 float32 ulps of margin): every later step shrinks p
+__device__ __forceinline__ bool rate_below(float lambda, float m) {
+    return __float_as_uint(lambda) + 16u < __float_as_uint(m) && lambda > 0.0f && m > 0.0f;
+}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Fast-window test on the high word: lo <= hi(p) < lo + span.
@@ -178,7 +186,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     const double tail_b = tab[4 * nh];
     bool bail = !in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail_b, kHiRateLo, kHiRateHi) ||
                 !in_window(A.b, kHiRateLo, kHiRateHi);
-    const bool tail_mono = (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tail_b);
+    const bool tail_mono = rate_below(lambda, (float)tail_b);
 
     double p = bail ? 0.0 : div_recip(lam, A);  // p[1]; RN(1*lambda) = lambda
     if (!(p >= 0.0) || (unsigned)__double2hiint(p) >= kHiPHi) bail = true;
@@ -188,6 +196,28 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     // merged fast window [max(thr, 2^-280), 2^600): inside it the step is a plain reciprocal step
     const unsigned lo_eff = thr_hi > kHiPLo ? thr_hi : kHiPLo;
     const unsigned span_eff = kHiPHi - lo_eff;
+
+    // 4-step blocks with ONE window test: a step multiplies p by lambda/servRate[.] which lies in
+    // [lambda/max rate, lambda/min rate] = [2^e_lo, 2^e_hi) (exponent arithmetic, conservative), so if
+    // p starts a block inside [2^-279 / 2^(3 e_lo), 2^600 / 2^(3 max(e_hi,0))) it stays inside the
+    // validity window of the reciprocal division for the whole block.  A chain that becomes negligible
+    // inside a block simply runs to the end of the block: those states add nothing.
+    unsigned blk_lo = 1, blk_span = 0;  // empty window = blocks disabled
+    {
+        const float smax = tab_prefix_max(tab, nh), smin = tab_suffix_min(tab, 0);
+        if (!bail && smin > 0.0f && smax >= smin) {
+            // lambda/smax >= 2^(El - Ex - 1),  lambda/smin < 2^(El - En + 1)   (E = biased float32 exponents)
+            const int El = (int)(__float_as_uint(lambda) >> 23), Ex = (int)(__float_as_uint(smax) >> 23),
+                      En = (int)(__float_as_uint(smin) >> 23);
+            const int e_lo = El - Ex - 1, e_hi = El - En + 1;
+            const int lo_exp = -279 - 3 * (e_lo < 0 ? e_lo : 0), hi_exp = 600 - 3 * (e_hi > 0 ? e_hi : 0);
+            if (lo_exp < hi_exp && lo_exp > -1000 && hi_exp > -1000) {
+                const unsigned lo4 = WVA_HI(lo_exp), hi4 = WVA_HI(hi_exp);
+                blk_lo = lo4 > lo_eff ? lo4 : lo_eff;
+                blk_span = hi4 > blk_lo ? hi4 - blk_lo : 0;
+            }
+        }
+    }
 
     // ---- pass 1 -----------------------------------------------------------------
     double sum = __dadd_rn(1.0, p);
@@ -200,27 +230,33 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             // (re-)establish: A = triple of step n, B = triple of step n+1
             load_recip(tab, n < nh ? n : nh, A);
             load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
+#define WVA_P1_STEP(R)                                                      \
+    p = div_recip(__dmul_rn(p, lam), R);                                    \
+    if (n < nh) load_recip(tab, n + 2 < nh ? n + 2 : nh, R);                \
+    sum = __dadd_rn(sum, p);                                                \
+    if (STASH > 0 && n < STASH) stash[n * 32] = p;                          \
+    ++n;
+            // all lanes that are still in this loop take the block path together or not at all: a lane
+            // on the per-step path next to lanes on the block path would serialise the warp
+            while (__all_sync(__activemask(), n + 4 <= n_stop && WVA_FASTWIN(p, blk_lo, blk_span))) {
+                if (n < nh) prefetch_l1(tab + 4 * (n + PF));
+                WVA_P1_STEP(A)
+                WVA_P1_STEP(B)
+                WVA_P1_STEP(A)
+                WVA_P1_STEP(B)
+            }
             for (;;) {
                 if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) break;
-                if (n < nh) {  // triple of step n+2 (B already holds n+1); prefetch two lines ahead
-                    prefetch_l1(tab + 4 * (n + PF));
-                }
-                p = div_recip(__dmul_rn(p, lam), A);
-                if (n < nh) load_recip(tab, n + 2 < nh ? n + 2 : nh, A);
-                sum = __dadd_rn(sum, p);
-                if (STASH > 0 && n < STASH) stash[n * 32] = p;  // state n+1
-                ++n;
+                if (n < nh) prefetch_l1(tab + 4 * (n + PF));
+                WVA_P1_STEP(A)
                 if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) break;
-                p = div_recip(__dmul_rn(p, lam), B);
-                if (n < nh) load_recip(tab, n + 2 < nh ? n + 2 : nh, B);
-                sum = __dadd_rn(sum, p);
-                if (STASH > 0 && n < STASH) stash[n * 32] = p;
-                ++n;
+                WVA_P1_STEP(B)
             }
+#undef WVA_P1_STEP
             if (n >= n_stop) break;
             // p[n] is outside the fast window
             const unsigned hp = (unsigned)__double2hiint(p);
-            if (hp < thr_hi && (n >= nh ? tail_mono : (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tab[4 * n + 3]))) {
+            if (hp < thr_hi && (n >= nh ? tail_mono : rate_below(lambda, tab_suffix_min(tab, n)))) {
                 j_end = n + 1;  // negligible and past the mode: states > n contribute nothing
                 break;
             }
@@ -247,6 +283,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     z.yl = __dmul_rn(__fma_rn(-sum, z.yh, 1.0), z.yh);
     double acc = 0.0, sum_p = z.yh, pn = 0.0, di = 1.0, acc_at_N = 0.0;
     p = p1;
+    // pass 2 uses the same block window (its lower edge is >= 2^-279 / 2^(3 e_lo), all the division needs)
+    const unsigned blk2_lo = blk_lo, blk2_span = blk_span;
     __syncwarp(warp_mask);
     {
         int i = 1;  // p holds p[i]
@@ -279,33 +317,35 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         while (i < j_end) {
             load_recip(tab, i < nh ? i : nh, A);  // triple of the step out of state i
             load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
+#define WVA_P2_STEP(R)                                                      \
+    {                                                                       \
+        const double a_ = __dmul_rn(p, lam);                                \
+        pn = div_recip(p, z);                                               \
+        p = div_recip(a_, R); /* p[i+1] (unused after the last state) */    \
+        if (i < nh) load_recip(tab, i + 2 < nh ? i + 2 : nh, R);            \
+        acc = __dadd_rn(acc, __dmul_rn(di, pn));                            \
+        di = __dadd_rn(di, 1.0);                                            \
+        if (i <= N) {                                                       \
+            sum_p = __dadd_rn(sum_p, pn);                                   \
+            acc_at_N = acc;                                                 \
+        }                                                                   \
+        ++i;                                                                \
+    }
+            while (__all_sync(__activemask(), i + 4 <= j_end && WVA_FASTWIN(p, blk2_lo, blk2_span))) {
+                if (i < nh) prefetch_l1(tab + 4 * (i + PF));
+                WVA_P2_STEP(A)
+                WVA_P2_STEP(B)
+                WVA_P2_STEP(A)
+                WVA_P2_STEP(B)
+            }
             for (;;) {
                 if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
                 if (i < nh) prefetch_l1(tab + 4 * (i + PF));
-                pn = div_recip(p, z);
-                const double a0 = __dmul_rn(p, lam);
-                acc = __dadd_rn(acc, __dmul_rn(di, pn));
-                di = __dadd_rn(di, 1.0);
-                if (i <= N) {
-                    sum_p = __dadd_rn(sum_p, pn);
-                    acc_at_N = acc;
-                }
-                p = div_recip(a0, A);  // p[i+1] (unused after the last state)
-                if (i < nh) load_recip(tab, i + 2 < nh ? i + 2 : nh, A);
-                ++i;
+                WVA_P2_STEP(A)
                 if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
-                pn = div_recip(p, z);
-                const double a1 = __dmul_rn(p, lam);
-                acc = __dadd_rn(acc, __dmul_rn(di, pn));
-                di = __dadd_rn(di, 1.0);
-                if (i <= N) {
-                    sum_p = __dadd_rn(sum_p, pn);
-                    acc_at_N = acc;
-                }
-                p = div_recip(a1, B);
-                if (i < nh) load_recip(tab, i + 2 < nh ? i + 2 : nh, B);
-                ++i;
+                WVA_P2_STEP(B)
             }
+#undef WVA_P2_STEP
             if (i >= j_end) break;
             if (p == 0.0) { pn = 0.0; break; }
             // rare: tiny p, exact IEEE divisions
@@ -364,15 +404,18 @@ __device__ __noinline__ bool solve_row(const double* __restrict__ tab, int len, 
     const unsigned span_eff = kHiPHi - lo_eff;
     double sum = __dadd_rn(1.0, p);
     int n = 1;
+    Recip B;
+    load_recip(tab, 1, A);  // triple of step n, loaded one step ahead of its use
     while (n < nh && WVA_FASTWIN(p, lo_eff, span_eff)) {
-        load_recip(tab, n, A);
+        load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
         p = div_recip(__dmul_rn(p, lam), A);
         sum = __dadd_rn(sum, p);
+        A = B;
         ++n;
     }
     if (n >= nh) return false;  // still alive at the end of the table
     const unsigned hp = (unsigned)__double2hiint(p);
-    const bool negligible = hp < thr_hi && (unsigned)__double2hiint(lam) < (unsigned)__double2hiint(tab[4 * n + 3]);
+    const bool negligible = hp < thr_hi && rate_below(lambda, tab_suffix_min(tab, n));
     if (!negligible && !(p == 0.0)) return false;
     if (!in_window(sum, kHiSumLo, kHiSumHi)) return false;
     j_last = n;
@@ -382,17 +425,19 @@ __device__ __noinline__ bool solve_row(const double* __restrict__ tab, int len, 
     z.yl = __dmul_rn(__fma_rn(-sum, z.yh, 1.0), z.yh);
     double acc = 0.0, sum_p = z.yh, di = 1.0;
     p = p1;
+    load_recip(tab, 1, A);
     for (int i = 1; i <= j_last; ++i) {
         if (!WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) {
             if (p == 0.0) break;  // adds nothing (the cell's pass 2 stops here as well)
             return false;
         }
+        load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
         const double pn = div_recip(p, z);
         acc = __dadd_rn(acc, __dmul_rn(di, pn));
         di = __dadd_rn(di, 1.0);
         sum_p = __dadd_rn(sum_p, pn);
-        load_recip(tab, i, A);
         p = div_recip(__dmul_rn(p, lam), A);
+        A = B;
     }
     acc_out = acc;
     sump_out = sum_p;

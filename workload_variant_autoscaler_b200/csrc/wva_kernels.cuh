@@ -169,8 +169,8 @@ __device__ __forceinline__ Cand zero_load_alloc(const DevFleet& f, int s, int a)
 }
 
 // ---------------------------------------------------------------------------
-// Shared head tables: entry n (0-based) of table t = {servRate[n], yh, yl, min(servRate[n..len-1])}
-// as doubles (32 B, two 16 B loads per head step), plus a float column
+// Shared head tables: entry n (0-based) of table t = {servRate[n], yh, yl} as doubles + {min(servRate[n..]),
+// max(servRate[0..n])} as floats (32 B, two 16 B loads per head step), plus a float column
 // ls[n] = sum_{i<n} log2(servRate[i]) used only to ESTIMATE chain lengths for scheduling.
 // ---------------------------------------------------------------------------
 // Per (table, batch index) constants shared by the 64 replica levels of a pair:
@@ -224,27 +224,50 @@ __global__ void __launch_bounds__(128) build_pair_tables(DevFleet f, const int* 
         __syncthreads();
     }
     if (l && threadIdx.x == 0) l[len] = (float)carry_s;
-    // backward sweep: suffix minimum of servRate (a NaN rate poisons it to 0 = early exit disabled)
-    __shared__ double wmin[4];
-    __shared__ double carry_m;
-    if (threadIdx.x == 0) carry_m = out[4 * (len - 1)];
+    // column 4 = {float suffix minimum, float prefix maximum} of servRate (exact: the rates are float32).
+    // A NaN rate poisons the suffix minimum to 0 (early exit disabled) and the prefix maximum to +inf.
+    __shared__ float wmin[4];
+    __shared__ float carry_m;
+    if (threadIdx.x == 0) carry_m = 3.402823466e38f;
     __syncthreads();
-    for (int base = 0; base < len; base += blockDim.x) {
-        const int n = len - 1 - (base + threadIdx.x);  // thread 0 takes the last entry
-        double v = n >= 0 ? out[4 * n] : 1.7976931348623157e308;
-        if (!(v == v)) v = 0.0;
-        double m = v;  // inclusive scan of min over lower thread ids (= higher n)
+    for (int base = 0; base < len; base += blockDim.x) {  // backward: suffix minimum
+        const int n = len - 1 - (base + threadIdx.x);     // thread 0 takes the last entry
+        float v = n >= 0 ? (float)out[4 * n] : 3.402823466e38f;
+        if (!(v == v)) v = 0.0f;
+        float m = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const double o = __shfl_up_sync(0xffffffffu, m, d);
-            if (lane >= d) m = fmin(m, o);
+            const float o = __shfl_up_sync(0xffffffffu, m, d);
+            if (lane >= d) m = fminf(m, o);
         }
         if (lane == 31) wmin[warp] = m;
         __syncthreads();
-        double pre = carry_m;
-        for (int w = 0; w < warp; ++w) pre = fmin(pre, wmin[w]);
-        m = fmin(m, pre);
-        if (n >= 0) out[4 * n + 3] = m;
+        float pre = carry_m;
+        for (int w = 0; w < warp; ++w) pre = fminf(pre, wmin[w]);
+        m = fminf(m, pre);
+        if (n >= 0) ((float*)(out + 4 * n + 3))[0] = m;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_m = m;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) carry_m = 0.0f;
+    __syncthreads();
+    for (int base = 0; base < len; base += blockDim.x) {  // forward: prefix maximum
+        const int n = base + threadIdx.x;
+        float v = n < len ? (float)out[4 * n] : 0.0f;
+        if (!(v == v)) v = 3.402823466e38f;
+        float m = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float o = __shfl_up_sync(0xffffffffu, m, d);
+            if (lane >= d) m = fmaxf(m, o);
+        }
+        if (lane == 31) wmin[warp] = m;
+        __syncthreads();
+        float pre = carry_m;
+        for (int w = 0; w < warp; ++w) pre = fmaxf(pre, wmin[w]);
+        m = fmaxf(m, pre);
+        if (n < len) ((float*)(out + 4 * n + 3))[1] = m;
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) carry_m = m;
         __syncthreads();
@@ -396,24 +419,47 @@ __device__ __forceinline__ void store_cell(const GridArgs& g, long long cell, in
     if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
 }
 
-// One lane per (server, accelerator, replica level): the chain every large-enough batch size shares.
+// One CTA per (server, accelerator) pair, one lane per replica level: the chain every large-enough
+// batch size shares.  The pair's table is staged in shared memory first (coalesced), so the serial
+// chains read it at shared-memory latency instead of waiting for L2 on every step.
+constexpr int kRowsSmemEntries = 1536;  // 48 KB of 32-byte entries; longer tables are read from global
 __global__ void __launch_bounds__(128) grid_rows(GridArgs g) {
+    extern __shared__ double rows_tab[];
     const DevFleet& f = g.f;
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= f.S * f.A * g.R) return;
-    const int sa = row / g.R, ri = row - sa * g.R;
+    const int sa = blockIdx.x;
     const int s = sa / f.A;
-    int j = INT_MAX;
-    double acc = 0.0, sump = 0.0;
     const long long toff = g.pair_tab_off[sa];
-    const float4 rt = g.rt[s * g.R + ri];
-    if (toff >= 0 && rt.x > 0.0f) {
-        int jl = 0;
-        if (solve_row(g.tab + 4 * toff, g.Bmax, rt.y, acc, sump, jl)) j = jl;
+    const double* tab = toff >= 0 ? g.tab + 4 * toff : nullptr;
+    const bool staged = toff >= 0 && g.Bmax <= kRowsSmemEntries;
+    if (staged) {
+        const double2* src = (const double2*)tab;
+        double2* dst = (double2*)rows_tab;
+        for (int i = threadIdx.x; i < 2 * g.Bmax; i += blockDim.x) dst[i] = src[i];
     }
-    g.row_j[row] = j;
-    g.row_acc[row] = acc;
-    g.row_sump[row] = sump;
+    __syncthreads();
+    const double* use = staged ? rows_tab : tab;
+    float l2s0 = 0.f, ls_end = 0.f;
+    if (toff >= 0) {
+        l2s0 = log2f((float)tab[0]);
+        ls_end = (g.ls + toff + g.pair_tab_idx[sa])[g.Bmax - 1];
+    }
+    for (int ri = threadIdx.x; ri < g.R; ri += blockDim.x) {
+        const size_t row = (size_t)sa * g.R + ri;
+        int j = INT_MAX;
+        double acc = 0.0, sump = 0.0;
+        const float4 rt = g.rt[s * g.R + ri];
+        if (toff >= 0 && rt.x > 0.0f) {
+            // skip rows whose chain is (by the log-domain estimate) still far from negligible at the end of
+            // the table: they cannot be shared and would only burn Bmax steps to find that out
+            const float thr = -78.0f + fminf(0.0f, rt.z - l2s0);
+            const float Lend = (float)(g.Bmax - 1) * rt.z - ls_end;
+            int jl = 0;
+            if (Lend < thr + 8.0f && solve_row(use, g.Bmax, rt.y, acc, sump, jl)) j = jl;
+        }
+        g.row_j[row] = j;
+        g.row_acc[row] = acc;
+        g.row_sump[row] = sump;
+    }
 }
 
 // Counter increment for lanes whose equal keys sit in CONTIGUOUS lane ranges (along a row the
