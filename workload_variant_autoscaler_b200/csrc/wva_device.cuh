@@ -203,6 +203,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     // validity window of the reciprocal division for the whole block.  A chain that becomes negligible
     // inside a block simply runs to the end of the block: those states add nothing.
     unsigned blk_lo = 1, blk_span = 0;  // empty window = blocks disabled
+    unsigned blk16_lo = 1, blk16_span = 0;
     {
         const float smax = tab_prefix_max(tab, nh), smin = tab_suffix_min(tab, 0);
         if (!bail && smin > 0.0f && smax >= smin) {
@@ -215,6 +216,13 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 const unsigned lo4 = WVA_HI(lo_exp), hi4 = WVA_HI(hi_exp);
                 blk_lo = lo4 > lo_eff ? lo4 : lo_eff;
                 blk_span = hi4 > blk_lo ? hi4 - blk_lo : 0;
+            }
+            // the same for 16-step blocks (15 unchecked steps)
+            const int lo_exp16 = -279 - 15 * (e_lo < 0 ? e_lo : 0), hi_exp16 = 600 - 15 * (e_hi > 0 ? e_hi : 0);
+            if (lo_exp16 < hi_exp16 && lo_exp16 > -1000 && hi_exp16 > -1000) {
+                const unsigned lo16 = WVA_HI(lo_exp16), hi16 = WVA_HI(hi_exp16);
+                blk16_lo = lo16 > lo_eff ? lo16 : lo_eff;
+                blk16_span = hi16 > blk16_lo ? hi16 - blk16_lo : 0;
             }
         }
     }
@@ -236,14 +244,31 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     sum = __dadd_rn(sum, p);                                                \
     if (STASH > 0 && n < STASH) stash[n * 32] = p;                          \
     ++n;
-            // all lanes that are still in this loop take the block path together or not at all: a lane
-            // on the per-step path next to lanes on the block path would serialise the warp
-            while (__all_sync(__activemask(), n + 4 <= n_stop && WVA_FASTWIN(p, blk_lo, blk_span))) {
-                if (n < nh) prefetch_l1(tab + 4 * (n + PF));
-                WVA_P1_STEP(A)
-                WVA_P1_STEP(B)
-                WVA_P1_STEP(A)
-                WVA_P1_STEP(B)
+            // Block phase.  All lanes that are still in this loop take a block path together or not at all
+            // (a lane on the per-step path next to lanes on a block path would serialise the warp).
+            //  * pure-tail 16-step blocks: every lane is past its table head (and past the stash), so a step
+            //    is just the recurrence and the running sum — no loads, no selects; this is where the long
+            //    chains spend 10/11 of their steps;
+            //  * generic 4-step blocks otherwise.
+            for (;;) {
+                if (__all_sync(__activemask(), n > nh + 1 && n >= STASH && n + 16 <= n_stop && WVA_FASTWIN(p, blk16_lo, blk16_span))) {
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        p = div_recip(__dmul_rn(p, lam), A);
+                        sum = __dadd_rn(sum, p);
+                    }
+                    n += 16;
+                    continue;
+                }
+                if (__all_sync(__activemask(), n + 4 <= n_stop && WVA_FASTWIN(p, blk_lo, blk_span))) {
+                    if (n < nh) prefetch_l1(tab + 4 * (n + PF));
+                    WVA_P1_STEP(A)
+                    WVA_P1_STEP(B)
+                    WVA_P1_STEP(A)
+                    WVA_P1_STEP(B)
+                    continue;
+                }
+                break;
             }
             for (;;) {
                 if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) break;
@@ -331,12 +356,28 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         }                                                                   \
         ++i;                                                                \
     }
-            while (__all_sync(__activemask(), i + 4 <= j_end && WVA_FASTWIN(p, blk2_lo, blk2_span))) {
-                if (i < nh) prefetch_l1(tab + 4 * (i + PF));
-                WVA_P2_STEP(A)
-                WVA_P2_STEP(B)
-                WVA_P2_STEP(A)
-                WVA_P2_STEP(B)
+            for (;;) {  // block phase, as in pass 1; pure-tail also needs i > N (sumP complete)
+                if (__all_sync(__activemask(), i > nh + 1 && i > N && i + 16 <= j_end && WVA_FASTWIN(p, blk16_lo, blk16_span))) {
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const double a_ = __dmul_rn(p, lam);
+                        pn = div_recip(p, z);
+                        p = div_recip(a_, A);
+                        acc = __dadd_rn(acc, __dmul_rn(di, pn));
+                        di = __dadd_rn(di, 1.0);
+                    }
+                    i += 16;
+                    continue;
+                }
+                if (__all_sync(__activemask(), i + 4 <= j_end && WVA_FASTWIN(p, blk2_lo, blk2_span))) {
+                    if (i < nh) prefetch_l1(tab + 4 * (i + PF));
+                    WVA_P2_STEP(A)
+                    WVA_P2_STEP(B)
+                    WVA_P2_STEP(A)
+                    WVA_P2_STEP(B)
+                    continue;
+                }
+                break;
             }
             for (;;) {
                 if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
@@ -521,6 +562,7 @@ struct Metrics {
 };
 __device__ __forceinline__ Metrics metrics_from(const QParams& q, int N, const ModelStats& st) {
     Metrics m;
+
     const float eff = effective_concurrency(q, st.avg_serv_time, N);
     m.avg_prefill_time = prefill_time(q, eff);
     m.avg_token_time = decode_time(q, eff);
