@@ -779,6 +779,7 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
         CK(h->d_dbg.ensure(sizeof(unsigned) * nc * 2));
         CK(cudaMemsetAsync(h->d_dbg.p, 0, sizeof(unsigned) * nc * 2, h->stream));
         g.dbg_cycles = (unsigned*)h->d_dbg.p;
+        g.dbg_n = nc;
         h->dbg_n = nc;
     }
     plan->Bmax = Bmax;
@@ -1513,7 +1514,7 @@ long long wva_dbg_read_cycles(wva_handle* h, unsigned* cycles, unsigned* cells, 
     if (!h || !h->d_dbg.p) return 0;
     const long long n = std::min<long long>((long long)h->dbg_n, cap);
     cudaMemcpy(cycles, h->d_dbg.p, sizeof(unsigned) * n, cudaMemcpyDeviceToHost);
-    cudaMemcpy(cells, h->d_sort.p, sizeof(unsigned) * n, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cells, (unsigned*)h->d_dbg.p + h->dbg_n, sizeof(unsigned) * n, cudaMemcpyDeviceToHost);
     return n;
 }
 

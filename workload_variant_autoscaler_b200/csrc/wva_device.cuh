@@ -234,10 +234,10 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     {
         int n = 1;  // p holds p[n]
         const int n_stop = bail ? 0 : K;
+        // invariant at the top of the loop: A = triple of step n, B = triple of step n+1
+        load_recip(tab, n < nh ? n : nh, A);
+        load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
         while (n < n_stop) {
-            // (re-)establish: A = triple of step n, B = triple of step n+1
-            load_recip(tab, n < nh ? n : nh, A);
-            load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
 #define WVA_P1_STEP(R)                                                      \
     p = div_recip(__dmul_rn(p, lam), R);                                    \
     if (n < nh) load_recip(tab, n + 2 < nh ? n + 2 : nh, R);                \
@@ -270,14 +270,19 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 }
                 break;
             }
-            for (;;) {
-                if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) break;
+            // Per-step phase: at most two checked steps, then back to the vote — the lane that failed the
+            // block vote (near its end, or p about to leave the window) is usually gone by then and the
+            // others must not stay on this slower path for the rest of their chain.
+            {
+                if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) goto p1_slow;
                 if (n < nh) prefetch_l1(tab + 4 * (n + PF));
                 WVA_P1_STEP(A)
-                if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) break;
+                if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) goto p1_slow;
                 WVA_P1_STEP(B)
+                continue;
             }
 #undef WVA_P1_STEP
+        p1_slow:
             if (n >= n_stop) break;
             // p[n] is outside the fast window
             const unsigned hp = (unsigned)__double2hiint(p);
@@ -293,6 +298,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             sum = __dadd_rn(sum, p);
             if (STASH > 0 && n < STASH) stash[n * 32] = p;
             ++n;
+            load_recip(tab, n < nh ? n : nh, A);
+            load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
         }
     }
     __syncwarp(warp_mask);
@@ -339,9 +346,10 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                                                                  : __ddiv_rn(__dmul_rn(pprev, lam), A.b);
             }
         }
+        // invariant at the top of the loop: A = triple of the step out of state i, B = of state i+1
+        load_recip(tab, i < nh ? i : nh, A);
+        load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
         while (i < j_end) {
-            load_recip(tab, i < nh ? i : nh, A);  // triple of the step out of state i
-            load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
 #define WVA_P2_STEP(R)                                                      \
     {                                                                       \
         const double a_ = __dmul_rn(p, lam);                                \
@@ -379,14 +387,16 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 }
                 break;
             }
-            for (;;) {
-                if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
+            {  // per-step phase: two checked steps, then back to the vote (see pass 1)
+                if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) goto p2_slow;
                 if (i < nh) prefetch_l1(tab + 4 * (i + PF));
                 WVA_P2_STEP(A)
-                if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
+                if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) goto p2_slow;
                 WVA_P2_STEP(B)
+                continue;
             }
 #undef WVA_P2_STEP
+        p2_slow:
             if (i >= j_end) break;
             if (p == 0.0) { pn = 0.0; break; }
             // rare: tiny p, exact IEEE divisions
@@ -400,6 +410,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             }
             p = __ddiv_rn(__dmul_rn(p, lam), A.b);
             ++i;
+            load_recip(tab, i < nh ? i : nh, A);
+            load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
         }
     }
     __syncwarp(warp_mask);

@@ -345,6 +345,7 @@ struct GridArgs {
     long long* fb_cells;
     int fb_cap;
     unsigned* dbg_cycles;    // diagnostics: per order index, SM cycles spent in grid_kernel (or NULL)
+    size_t dbg_n;            // cells; dbg_cycles[dbg_n + idx] holds the warp timeline (start ns, SM, end ns)
 };
 
 __device__ __forceinline__ void decode_cell(const GridArgs& g, long long cell, int& s, int& a, int& bi, int& ri) {
@@ -612,6 +613,8 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const unsigned long long item = g.items_sorted[w];
     if (lane >= (unsigned)((item >> 32) & 0xff)) return;
     const long long t_start = g.dbg_cycles ? clock64() : 0;
+    unsigned long long t_start_ns = 0;
+    if (g.dbg_cycles) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start_ns));
     const long long cell = g.order[(unsigned)item + lane];
     int s, a, bi, ri;
     decode_cell(g, cell, s, a, bi, ri);
@@ -636,7 +639,16 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const bool feas = cell_feasible(f, s, r, rate, rmax, m);
     store_cell(g, cell, 1, feas ? 1 : 0, m);
     if (feas) atomicMin(&g.best_rank[((size_t)s * f.A + a) * g.R + ri], g.batch_rank[bi]);
-    if (g.dbg_cycles) g.dbg_cycles[idx] = (unsigned)(clock64() - t_start);
+    if (g.dbg_cycles) {
+        g.dbg_cycles[idx] = (unsigned)(clock64() - t_start);
+        if (lane < 3) {  // timeline: [0] start ns, [1] SM id, [2] end ns (low 32 bits of %globaltimer)
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+            unsigned smid;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            g.dbg_cycles[g.dbg_n + idx] = lane == 0 ? (unsigned)t_start_ns : lane == 1 ? smid : (unsigned)t_end;
+        }
+    }
 }
 
 // Stored-vector re-run of bailed cells. One thread per slot; slot k handles cells
