@@ -49,7 +49,7 @@ for a, b in zip(edges[:-1], edges[1:]):
     print("t=%6.1f us resident warps %6d (%.1f / SM)" % (mid / 1e3, res, res / 148))
 # launch-order view: duration of warps by launch index
 idx = np.nonzero(ok)[0]
-for lo in (0, 1000, 2000, 3552, 5000, 8000, 12000, 16000, 20000):
-    sel = (idx >= lo) & (idx < lo + 200)
+for lo in (0, 50, 100, 150, 200, 300, 400, 500, 600, 800, 1000, 1500, 2000, 3000, 3552, 5000, 8000, 12000, 16000, 20000):
+    sel = (idx >= lo) & (idx < lo + 50)
     if sel.any():
-        print("warps %6d..: start %.1f us dur %.1f us (max %.1f)" % (lo, start[sel].mean() / 1e3, dur[sel].mean() / 1e3, dur[sel].max() / 1e3))
+        print("warps %6d..: start %.1f us dur %.1f us (max %.1f) cycles/lane mean %.0f" % (lo, start[sel].mean() / 1e3, dur[sel].mean() / 1e3, dur[sel].max() / 1e3, cw[sel].mean()))

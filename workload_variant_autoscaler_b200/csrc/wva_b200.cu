@@ -775,6 +775,17 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     g.fb_cap = (int)std::min<size_t>(nc, (size_t)1 << 22);
     CK(h->d_fb_list.ensure(sizeof(long long) * g.fb_cap));
     g.fb_cells = (long long*)h->d_fb_list.p;
+    {
+        // grid_kernel's long queue: items of at least ~min_len states, at most long_per_sm per SM
+        int long_per_sm = kGkLong, min_len = 1024;
+        if (const char* e = getenv("WVA_GRID_LONG")) long_per_sm = std::min(std::max(atoi(e), 0), kGkWarps / 4);
+        if (const char* e = getenv("WVA_GRID_LONG_MINLEN")) min_len = std::max(atoi(e), 2);
+        g.long_per_sm = long_per_sm;
+        g.long_share = 0;
+        if (const char* e = getenv("WVA_GRID_SHARE")) g.long_share = std::max(atoi(e), 0);
+        g.long_cls = 254 - std::min(std::max((int)(log2f((float)min_len) * 12.0f), 0), 254);
+        g.long_cap = (unsigned)(long_per_sm * h->sm_count);
+    }
     if (h->dbg_cycles) {
         CK(h->d_dbg.ensure(sizeof(unsigned) * nc * 2));
         CK(cudaMemsetAsync(h->d_dbg.p, 0, sizeof(unsigned) * nc * 2, h->stream));
@@ -798,7 +809,7 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
     if (plan.n_cells > 0) {
         CK(cudaMemsetAsync(g.cells.flags, 0, plan.n_cells, h->stream));
         fill_int<<<(unsigned)((n_best + 255) / 256), 256, 0, h->stream>>>(g.best_rank, n_best, INT_MAX);
-        CK(cudaMemsetAsync(g.item_count, 0, sizeof(unsigned) * (2 * kClasses + 1), h->stream));
+        CK(cudaMemsetAsync(g.item_count, 0, sizeof(unsigned) * (2 * kClasses + 8), h->stream));
         {
             const int rows_threads = g.R >= 128 ? 128 : (g.R > 32 ? 64 : 32);
             const size_t rows_smem = g.Bmax <= kRowsSmemEntries ? (size_t)g.Bmax * 32 : 0;
@@ -811,14 +822,9 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
         grid_items_scan<<<1, 256, 0, h->stream>>>(g);
         grid_items_scatter<<<(unsigned)((max_items + 255) / 256), 256, 0, h->stream>>>(g);
         h->launches++;
-        const unsigned blocks = (unsigned)((max_items * 32 + 255) / 256);
         CK(cudaEventRecord(h->ev_k0, h->stream));  // wva_last_kernel_ms = the dominant kernel alone
-        size_t smem = 8 * kGridStash * 32 * sizeof(double);
-        if (const char* e = getenv("WVA_GRID_SMEM_KB")) {  // experiment: cap the resident blocks per SM
-            smem = std::max<size_t>(smem, (size_t)atoi(e) * 1024);
-            cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        }
-        grid_kernel<<<blocks, 256, smem, h->stream>>>(g);
+        const size_t smem = (size_t)kGkWarps * (kGridStash * 32 + kGkTabWin * 4) * sizeof(double);
+        grid_kernel<<<(unsigned)h->sm_count, kGkThreads, smem, h->stream>>>(g);
         h->launches += 4;
     }
     CK(cudaEventRecord(h->ev_k1, h->stream));
@@ -1145,6 +1151,8 @@ int wva_create(wva_handle** out, int device) {
     h->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((size_t)kGkWarps * (kGridStash * 32 + kGkTabWin * 4) * sizeof(double)));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev_k0) != cudaSuccess || cudaEventCreate(&h->ev_k1) != cudaSuccess ||
         cudaEventCreate(&h->ev_d0) != cudaSuccess || cudaEventCreate(&h->ev_d1) != cudaSuccess) {
@@ -1505,6 +1513,12 @@ long long wva_dbg_div_selfcheck(wva_handle* h, unsigned long long seed, int bloc
     return (long long)out;
 }
 
+#ifdef WVA_PROF
+int wva_dbg_prof(long long* out, int reset) {
+    if (reset) { long long z[16] = {0}; return (int)cudaMemcpyToSymbol(wva::wva_prof, z, sizeof(z)); }
+    return (int)cudaMemcpyFromSymbol(out, wva::wva_prof, sizeof(long long) * 16);
+}
+#endif
 int wva_dbg_enable_cycles(wva_handle* h, int on) {
     if (!h) return WVA_ERR_BAD_ARG;
     h->dbg_cycles = on != 0;

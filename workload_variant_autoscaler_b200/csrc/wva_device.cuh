@@ -175,9 +175,25 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // STASH > 0: the first STASH states of pass 1 are kept in shared memory (stash[(j-1)*32] for
 // state j, one 8-byte column per lane) and pass 2 reads them back instead of re-running the
 // recurrence for those states — most grid chains are shorter than that.
-template <int STASH, int PF = 10>
+//
+#ifdef WVA_PROF  // diagnostics build (tools/prof_chain.py): phase clocks and counters of the last solve
+__device__ long long wva_prof[16];
+#define WVA_PROF_T(k) wva_prof[k] = clock64()
+#define WVA_PROF_C(k) ++wva_prof[k]
+#else
+#define WVA_PROF_T(k)
+#define WVA_PROF_C(k)
+#endif
+//
+// STAGED (grid_kernel): when the 32 lanes of a full warp read the SAME pair table (they usually do: an
+// item is cut from one pair's cells) the head of both passes runs from a 32-entry window of the table
+// that the warp stages in shared memory (`tbuf`, 1 KB per warp) with one coalesced load per 32 steps,
+// the next window prefetched meanwhile.  Per-lane global loads two steps ahead of their use leave
+// most of the L2 latency exposed (every table entry is its own 32-byte sector): ~160 cycles per head
+// step on an idle SM and 300+ on a busy one, against ~55 from the staged window (tools/head_bench.cu).
+template <int STASH, int PF = 10, bool STAGED = false>
 __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st,
-                                           double* __restrict__ stash) {
+                                           double* __restrict__ stash, double* __restrict__ tbuf = nullptr) {
     const unsigned warp_mask = __activemask();
     const double lam = (double)lambda;
     const int nh = N - 1;
@@ -228,12 +244,76 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     }
 
     // ---- pass 1 -----------------------------------------------------------------
+    WVA_PROF_T(0);
     double sum = __dadd_rn(1.0, p);
     int j_end = K + 1;
     if (STASH > 0) stash[0] = p;
+    // staged head: full warp, one table
+    bool staged = false;
+    int hmax = 0, hmin = 0;
+    if (STAGED) {
+        staged = warp_mask == 0xffffffffu && __all_sync(0xffffffffu, tab == (const double*)__shfl_sync(0xffffffffu, (unsigned long long)tab, 0));
+        if (staged) {
+            hmax = __reduce_max_sync(0xffffffffu, nh);
+            hmin = __reduce_min_sync(0xffffffffu, nh);
+        }
+    }
     {
         int n = 1;  // p holds p[n]
         const int n_stop = bail ? 0 : K;
+        if (STAGED && staged) {
+            // steps n < nh read entry n from the window, later steps the lane's own tail entry; all lanes
+            // hold the same n (they advance together or leave together).  A window in which every lane
+            // is still in its head (the usual case: grid_sort_local keeps cells of similar batch size
+            // together) needs no per-lane select; only the first window feeds the stash.
+            const double4* tab4 = reinterpret_cast<const double4*>(tab);
+            double4* tb = reinterpret_cast<double4*>(tbuf);
+            const int lane = threadIdx.x & 31;
+            Recip T;
+            load_recip(tab, nh, T);
+            bool ok = true;
+#define WVA_SP1(SEL, ST)                                                                                          \
+    _Pragma("unroll 1") for (int k = 0; k < 32; k += 4) {                                                         \
+        if (!__all_sync(0xffffffffu, n + 4 <= n_stop && WVA_FASTWIN(p, blk_lo, blk_span))) { ok = false; break; } \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                           \
+            const double4 e = tb[k + u];                                                                          \
+            Recip R;                                                                                              \
+            if (SEL) {                                                                                            \
+                const bool hd = n < nh;                                                                           \
+                R.b = hd ? e.x : T.b;                                                                             \
+                R.yh = hd ? e.y : T.yh;                                                                           \
+                R.yl = hd ? e.z : T.yl;                                                                           \
+            } else {                                                                                              \
+                R.b = e.x;                                                                                        \
+                R.yh = e.y;                                                                                       \
+                R.yl = e.z;                                                                                       \
+            }                                                                                                     \
+            p = div_recip(__dmul_rn(p, lam), R);                                                                  \
+            sum = __dadd_rn(sum, p);                                                                              \
+            if (ST && n < STASH) stash[n * 32] = p;                                                               \
+            ++n;                                                                                                  \
+        }                                                                                                         \
+    }
+            double4 nxt = tab4[min(1 + lane, hmax)];  // the next window travels in registers
+            for (int n0 = 1; ok && n0 < hmax; n0 += 32) {
+                WVA_PROF_C(4);
+                __syncwarp();
+                tb[lane] = nxt;
+                __syncwarp();
+                if (n0 + 32 < hmax) nxt = tab4[min(n0 + 32 + lane, hmax)];
+                const bool all_head = n0 + 32 <= hmin;
+                if (STASH > 0 && n0 < STASH) {
+                    if (all_head) { WVA_SP1(false, true) } else { WVA_SP1(true, true) }
+                } else {
+                    if (all_head) { WVA_SP1(false, false) } else { WVA_SP1(true, false) }
+                }
+            }
+#undef WVA_SP1
+        }
+        WVA_PROF_T(12);
+#ifdef WVA_PROF
+        wva_prof[5] = n;
+#endif
         // invariant at the top of the loop: A = triple of step n, B = triple of step n+1
         load_recip(tab, n < nh ? n : nh, A);
         load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
@@ -303,6 +383,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         }
     }
     __syncwarp(warp_mask);
+    WVA_PROF_T(1);
     if (!in_window(sum, kHiSumLo, kHiSumHi)) bail = true;
     if (bail) { sum = 1.0; j_end = 1; }
 
@@ -346,6 +427,63 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                                                                  : __ddiv_rn(__dmul_rn(pprev, lam), A.b);
             }
         }
+        WVA_PROF_T(2);
+        if (STAGED && staged && __all_sync(0xffffffffu, i == __shfl_sync(0xffffffffu, i, 0))) {
+            // staged head of pass 2 (see pass 1): states i < nh take their step's entry from the window
+            const double4* tab4 = reinterpret_cast<const double4*>(tab);
+            double4* tb = reinterpret_cast<double4*>(tbuf);
+            const int lane = threadIdx.x & 31;
+            Recip T;
+            load_recip(tab, nh, T);
+            bool ok = true;
+#define WVA_SP2(SEL)                                                                                              \
+    _Pragma("unroll 1") for (int k = 0; k < 32; k += 4) {                                                         \
+        if (!__all_sync(0xffffffffu, i + 4 <= j_end && WVA_FASTWIN(p, blk2_lo, blk2_span))) { ok = false; break; } \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                           \
+            const double4 e = tb[k + u];                                                                          \
+            Recip R;                                                                                              \
+            if (SEL) {                                                                                            \
+                const bool hd = i < nh;                                                                           \
+                R.b = hd ? e.x : T.b;                                                                             \
+                R.yh = hd ? e.y : T.yh;                                                                           \
+                R.yl = hd ? e.z : T.yl;                                                                           \
+            } else {                                                                                              \
+                R.b = e.x;                                                                                        \
+                R.yh = e.y;                                                                                       \
+                R.yl = e.z;                                                                                       \
+            }                                                                                                     \
+            const double a_ = __dmul_rn(p, lam);                                                                  \
+            pn = div_recip(p, z);                                                                                 \
+            p = div_recip(a_, R);                                                                                 \
+            acc = __dadd_rn(acc, __dmul_rn(di, pn));                                                              \
+            di = __dadd_rn(di, 1.0);                                                                              \
+            if (SEL) {                                                                                            \
+                if (i <= N) {                                                                                     \
+                    sum_p = __dadd_rn(sum_p, pn);                                                                 \
+                    acc_at_N = acc;                                                                               \
+                }                                                                                                 \
+            } else {                                                                                              \
+                sum_p = __dadd_rn(sum_p, pn); /* i < nh < N for every lane */                                     \
+            }                                                                                                     \
+            ++i;                                                                                                  \
+        }                                                                                                         \
+        if (!(SEL)) acc_at_N = acc;                                                                               \
+    }
+            double4 nxt = tab4[min(i + lane, hmax)];
+            for (int i0 = i; ok && i0 < hmax; i0 += 32) {
+                WVA_PROF_C(7);
+                __syncwarp();
+                tb[lane] = nxt;
+                __syncwarp();
+                if (i0 + 32 < hmax) nxt = tab4[min(i0 + 32 + lane, hmax)];
+                if (i0 + 32 <= hmin) { WVA_SP2(false) } else { WVA_SP2(true) }
+            }
+#undef WVA_SP2
+        }
+        WVA_PROF_T(13);
+#ifdef WVA_PROF
+        wva_prof[8] = i;
+#endif
         // invariant at the top of the loop: A = triple of the step out of state i, B = of state i+1
         load_recip(tab, i < nh ? i : nh, A);
         load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
@@ -415,6 +553,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         }
     }
     __syncwarp(warp_mask);
+    WVA_PROF_T(3);
     // acc_at_N tracked acc while i <= N: it holds acc at state min(N, last state)
     const double in_serv = __dadd_rn(acc_at_N, __dmul_rn(__dsub_rn(1.0, sum_p), (double)N));
     const double pnK = (j_end == K + 1) ? pn : 0.0;

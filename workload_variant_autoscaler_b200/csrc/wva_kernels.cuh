@@ -344,6 +344,10 @@ struct GridArgs {
     int* fb_count;           // cells that need the stored-vector fallback
     long long* fb_cells;
     int fb_cap;
+    int long_per_sm;         // grid_kernel: warps per SM (sub-partition 0) that pull the long queue
+    int long_share;          // ... and how many other warps of that sub-partition may pull short items meanwhile
+    int long_cls;            // items of class <= long_cls are "long" ...
+    unsigned long_cap;       // ... up to this many (long_per_sm x CTAs)
     unsigned* dbg_cycles;    // diagnostics: per order index, SM cycles spent in grid_kernel (or NULL)
     size_t dbg_n;            // cells; dbg_cycles[dbg_n + idx] holds the warp timeline (start ns, SM, end ns)
 };
@@ -590,11 +594,17 @@ __global__ void __launch_bounds__(256) grid_items_scan(GridArgs g) {
     tot[threadIdx.x] = g.item_count[1 + threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned acc = 0;
+        unsigned acc = 0, n_long = 0;
         for (int c = 0; c < kClasses; ++c) {
             g.item_count[1 + kClasses + c] = acc;
             acc += tot[c];
+            if (c <= g.long_cls) n_long = acc;  // items at least that long
         }
+        // grid_kernel's queues: the long queue is the head of the sorted list, the short queue the rest
+        n_long = min(n_long, g.long_cap);
+        g.item_count[2 * kClasses + 1] = n_long;
+        g.item_count[2 * kClasses + 2] = 0;
+        g.item_count[2 * kClasses + 3] = n_long;
     }
 }
 __global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
@@ -605,17 +615,36 @@ __global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
     g.items_sorted[agg_inc(g.item_count + 1 + kClasses, (int)((it >> 40) & 0xff))] = it;
 }
 
-__global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
+// ---------------------------------------------------------------------------
+// grid_kernel — persistent, one CTA of kGkWarps warps per SM, warps pull items (32 cells of similar
+// chain length) from two queues over the globally sorted item list:
+//   * the LONG queue = the first n_long items (the longest chains, at most kGkLong per SM).  Their
+//     latency bounds the launch: a 2816-state chain is 5632 dependent steps of >= 48 cycles, and
+//     under equal sharing of a saturated FP64 pipe it would run 2-3x slower.  Warp w issues on SM
+//     sub-partition w % 4 (tools/subpart_bench.cu), so the long items are pulled only by kGkLong
+//     warps of sub-partition 0 and the other warps of that sub-partition stay parked until this
+//     CTA's long warps are done: the long chains get a pipe to themselves;
+//   * the SHORT queue = everything else, longest first, pulled by all other warps (and by the
+//     sub-partition-0 warps once the CTA's long work is finished).
+// ---------------------------------------------------------------------------
+constexpr int kGkWarps = 16;    // 4 per sub-partition; 128 registers per thread keep the two FP64 chains of pass 2 apart
+constexpr int kGkThreads = kGkWarps * 32;
+constexpr int kGkTabWin = 32;  // table entries staged per warp (solve_shared_t STAGED)
+constexpr int kGkLong = 1;     // long-item warps per SM (sub-partition 0)
+constexpr int kQLongN = 2 * kClasses + 1, kQLongCtr = kQLongN + 1, kQShortCtr = kQLongN + 2;  // in item_count[]
+
+__device__ __forceinline__ void grid_item(const GridArgs& g, unsigned w, unsigned lane, double* stash_warp, double* tbuf_warp) {
     const DevFleet& f = g.f;
-    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned w = idx >> 5, lane = idx & 31;
-    if (w >= *g.item_count) return;
     const unsigned long long item = g.items_sorted[w];
-    if (lane >= (unsigned)((item >> 32) & 0xff)) return;
+    // a partial item (the last of a sort chunk) is padded with copies of its first cell so that the
+    // whole warp takes part in the staged table loads; the copies store nothing
+    const bool valid = lane < (unsigned)((item >> 32) & 0xff);
+    const unsigned idx = w * 32 + lane;
     const long long t_start = g.dbg_cycles ? clock64() : 0;
     unsigned long long t_start_ns = 0;
     if (g.dbg_cycles) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start_ns));
-    const long long cell = g.order[(unsigned)item + lane];
+    WVA_PROF_T(9);
+    const long long cell = g.order[(unsigned)item + (valid ? lane : 0u)];
     int s, a, bi, ri;
     decode_cell(g, cell, s, a, bi, ri);
     const int b = g.batch[bi], r = g.replicas[ri];
@@ -626,28 +655,66 @@ __global__ void __launch_bounds__(256) grid_kernel(GridArgs g) {
     const float4 rt = g.rt[s * g.R + ri];
     const float rate = rt.x, lambda = rt.y;
     ModelStats st;
-    extern __shared__ double grid_stash[];  // [warp][state][lane]
-    double* stash = grid_stash + (size_t)(threadIdx.x >> 5) * (kGridStash * 32) + (threadIdx.x & 31);
-    const int rc = solve_shared_t<kGridStash>(tab, N, K, lambda, st, stash);
-    if (rc != kSolveOk) {
-        const int k = atomicAdd(g.fb_count, 1);
-        if (k < g.fb_cap) g.fb_cells[k] = cell;
-        return;
-    }
-    const QParams q = qparams_of(f, s, a);
-    const Metrics m = metrics_from(q, N, st);
-    const bool feas = cell_feasible(f, s, r, rate, rmax, m);
-    store_cell(g, cell, 1, feas ? 1 : 0, m);
-    if (feas) atomicMin(&g.best_rank[((size_t)s * f.A + a) * g.R + ri], g.batch_rank[bi]);
-    if (g.dbg_cycles) {
-        g.dbg_cycles[idx] = (unsigned)(clock64() - t_start);
-        if (lane < 3) {  // timeline: [0] start ns, [1] SM id, [2] end ns (low 32 bits of %globaltimer)
-            unsigned long long t_end;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
-            unsigned smid;
-            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-            g.dbg_cycles[g.dbg_n + idx] = lane == 0 ? (unsigned)t_start_ns : lane == 1 ? smid : (unsigned)t_end;
+    WVA_PROF_T(10);
+    const int rc = solve_shared_t<kGridStash, 10, true>(tab, N, K, lambda, st, stash_warp + lane, tbuf_warp);
+    WVA_PROF_T(11);
+    if (valid) {
+        if (rc != kSolveOk) {
+            const int k = atomicAdd(g.fb_count, 1);
+            if (k < g.fb_cap) g.fb_cells[k] = cell;
+        } else {
+            const QParams q = qparams_of(f, s, a);
+            const Metrics m = metrics_from(q, N, st);
+            const bool feas = cell_feasible(f, s, r, rate, rmax, m);
+            store_cell(g, cell, 1, feas ? 1 : 0, m);
+            if (feas) atomicMin(&g.best_rank[((size_t)s * f.A + a) * g.R + ri], g.batch_rank[bi]);
+            if (g.dbg_cycles) {
+                g.dbg_cycles[idx] = (unsigned)(clock64() - t_start);
+                if (lane < 3) {  // timeline: [0] start ns, [1] SM id, [2] end ns (low 32 bits of %globaltimer)
+                    unsigned long long t_end;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+                    unsigned smid;
+                    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+                    g.dbg_cycles[g.dbg_n + idx] = lane == 0 ? (unsigned)t_start_ns : lane == 1 ? smid : (unsigned)t_end;
+                }
+            }
         }
+    }
+    __syncwarp();
+    WVA_PROF_T(14);
+}
+
+__global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
+    extern __shared__ double grid_stash[];  // [warp][state][lane]
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* stash_warp = grid_stash + (size_t)warp * (kGridStash * 32 + kGkTabWin * 4);
+    double* tbuf_warp = stash_warp + kGridStash * 32;  // 32 table entries of 4 doubles
+    const unsigned n_items = g.item_count[0], n_long = g.item_count[kQLongN];
+    const bool sub0 = (warp & 3) == 0;
+    const bool long_warp = sub0 && (warp >> 2) < (unsigned)g.long_per_sm;
+    // sub-partition 0: long_per_sm warps pull the long queue, long_share more may pull short items next
+    // to them, the rest wait on named barrier 1 (blocked in hardware: no issue slots) until the long warps
+    // of this CTA have drained the long queue
+    const int n_parked = kGkWarps / 4 - g.long_per_sm - g.long_share;
+    const int bar_threads = 32 * (g.long_per_sm + (n_parked > 0 ? n_parked : 0));
+    if (long_warp && n_long) {
+        for (;;) {
+            unsigned w = 0;
+            if (lane == 0) w = atomicAdd(g.item_count + kQLongCtr, 1u);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= n_long) break;
+            grid_item(g, w, lane, stash_warp, tbuf_warp);
+        }
+        if (n_parked > 0) asm volatile("bar.arrive 1, %0;" ::"r"(bar_threads) : "memory");
+    } else if (sub0 && n_long && !long_warp && (int)(warp >> 2) >= g.long_per_sm + g.long_share) {
+        asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+    }
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0) w = atomicAdd(g.item_count + kQShortCtr, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_items) break;
+        grid_item(g, w, lane, stash_warp, tbuf_warp);
     }
 }
 
