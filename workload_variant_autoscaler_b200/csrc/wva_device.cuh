@@ -272,27 +272,29 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             Recip T;
             load_recip(tab, nh, T);
             bool ok = true;
-#define WVA_SP1(SEL, ST)                                                                                          \
+#define WVA_SP1_GROUP(SEL, ST)                                                                                    \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                               \
+        const double4 e = tb[k + u];                                                                              \
+        Recip R;                                                                                                  \
+        if (SEL) {                                                                                                \
+            const bool hd = n < nh;                                                                               \
+            R.b = hd ? e.x : T.b;                                                                                 \
+            R.yh = hd ? e.y : T.yh;                                                                               \
+            R.yl = hd ? e.z : T.yl;                                                                               \
+        } else {                                                                                                  \
+            R.b = e.x;                                                                                            \
+            R.yh = e.y;                                                                                           \
+            R.yl = e.z;                                                                                           \
+        }                                                                                                         \
+        p = div_recip(__dmul_rn(p, lam), R);                                                                      \
+        sum = __dadd_rn(sum, p);                                                                                  \
+        if (ST && n < STASH) stash[n * 32] = p;                                                                   \
+        ++n;                                                                                                      \
+    }
+#define WVA_SP1(ST)                                                                                               \
     _Pragma("unroll 1") for (int k = 0; k < 32; k += 4) {                                                         \
         if (!__all_sync(0xffffffffu, n + 4 <= n_stop && WVA_FASTWIN(p, blk_lo, blk_span))) { ok = false; break; } \
-        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                           \
-            const double4 e = tb[k + u];                                                                          \
-            Recip R;                                                                                              \
-            if (SEL) {                                                                                            \
-                const bool hd = n < nh;                                                                           \
-                R.b = hd ? e.x : T.b;                                                                             \
-                R.yh = hd ? e.y : T.yh;                                                                           \
-                R.yl = hd ? e.z : T.yl;                                                                           \
-            } else {                                                                                              \
-                R.b = e.x;                                                                                        \
-                R.yh = e.y;                                                                                       \
-                R.yl = e.z;                                                                                       \
-            }                                                                                                     \
-            p = div_recip(__dmul_rn(p, lam), R);                                                                  \
-            sum = __dadd_rn(sum, p);                                                                              \
-            if (ST && n < STASH) stash[n * 32] = p;                                                               \
-            ++n;                                                                                                  \
-        }                                                                                                         \
+        if (n + 4 <= hmin) { WVA_SP1_GROUP(false, ST) } else { WVA_SP1_GROUP(true, ST) }                          \
     }
             double4 nxt = tab4[min(1 + lane, hmax)];  // the next window travels in registers
             for (int n0 = 1; ok && n0 < hmax; n0 += 32) {
@@ -301,13 +303,9 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 tb[lane] = nxt;
                 __syncwarp();
                 if (n0 + 32 < hmax) nxt = tab4[min(n0 + 32 + lane, hmax)];
-                const bool all_head = n0 + 32 <= hmin;
-                if (STASH > 0 && n0 < STASH) {
-                    if (all_head) { WVA_SP1(false, true) } else { WVA_SP1(true, true) }
-                } else {
-                    if (all_head) { WVA_SP1(false, false) } else { WVA_SP1(true, false) }
-                }
+                if (STASH > 0 && n0 < STASH) { WVA_SP1(true) } else { WVA_SP1(false) }
             }
+#undef WVA_SP1_GROUP
 #undef WVA_SP1
         }
         WVA_PROF_T(12);
@@ -436,38 +434,40 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             Recip T;
             load_recip(tab, nh, T);
             bool ok = true;
-#define WVA_SP2(SEL)                                                                                              \
+#define WVA_SP2_GROUP(SEL)                                                                                        \
+    _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                               \
+        const double4 e = tb[k + u];                                                                              \
+        Recip R;                                                                                                  \
+        if (SEL) {                                                                                                \
+            const bool hd = i < nh;                                                                               \
+            R.b = hd ? e.x : T.b;                                                                                 \
+            R.yh = hd ? e.y : T.yh;                                                                               \
+            R.yl = hd ? e.z : T.yl;                                                                               \
+        } else {                                                                                                  \
+            R.b = e.x;                                                                                            \
+            R.yh = e.y;                                                                                           \
+            R.yl = e.z;                                                                                           \
+        }                                                                                                         \
+        const double a_ = __dmul_rn(p, lam);                                                                      \
+        pn = div_recip(p, z);                                                                                     \
+        p = div_recip(a_, R);                                                                                     \
+        acc = __dadd_rn(acc, __dmul_rn(di, pn));                                                                  \
+        di = __dadd_rn(di, 1.0);                                                                                  \
+        if (SEL) {                                                                                                \
+            if (i <= N) {                                                                                         \
+                sum_p = __dadd_rn(sum_p, pn);                                                                     \
+                acc_at_N = acc;                                                                                   \
+            }                                                                                                     \
+        } else {                                                                                                  \
+            sum_p = __dadd_rn(sum_p, pn); /* i < nh < N for every lane */                                         \
+        }                                                                                                         \
+        ++i;                                                                                                      \
+    }                                                                                                             \
+    if (!(SEL)) acc_at_N = acc;
+#define WVA_SP2()                                                                                                 \
     _Pragma("unroll 1") for (int k = 0; k < 32; k += 4) {                                                         \
         if (!__all_sync(0xffffffffu, i + 4 <= j_end && WVA_FASTWIN(p, blk2_lo, blk2_span))) { ok = false; break; } \
-        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                           \
-            const double4 e = tb[k + u];                                                                          \
-            Recip R;                                                                                              \
-            if (SEL) {                                                                                            \
-                const bool hd = i < nh;                                                                           \
-                R.b = hd ? e.x : T.b;                                                                             \
-                R.yh = hd ? e.y : T.yh;                                                                           \
-                R.yl = hd ? e.z : T.yl;                                                                           \
-            } else {                                                                                              \
-                R.b = e.x;                                                                                        \
-                R.yh = e.y;                                                                                       \
-                R.yl = e.z;                                                                                       \
-            }                                                                                                     \
-            const double a_ = __dmul_rn(p, lam);                                                                  \
-            pn = div_recip(p, z);                                                                                 \
-            p = div_recip(a_, R);                                                                                 \
-            acc = __dadd_rn(acc, __dmul_rn(di, pn));                                                              \
-            di = __dadd_rn(di, 1.0);                                                                              \
-            if (SEL) {                                                                                            \
-                if (i <= N) {                                                                                     \
-                    sum_p = __dadd_rn(sum_p, pn);                                                                 \
-                    acc_at_N = acc;                                                                               \
-                }                                                                                                 \
-            } else {                                                                                              \
-                sum_p = __dadd_rn(sum_p, pn); /* i < nh < N for every lane */                                     \
-            }                                                                                                     \
-            ++i;                                                                                                  \
-        }                                                                                                         \
-        if (!(SEL)) acc_at_N = acc;                                                                               \
+        if (i + 4 <= hmin) { WVA_SP2_GROUP(false) } else { WVA_SP2_GROUP(true) }                                  \
     }
             double4 nxt = tab4[min(i + lane, hmax)];
             for (int i0 = i; ok && i0 < hmax; i0 += 32) {
@@ -476,8 +476,9 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 tb[lane] = nxt;
                 __syncwarp();
                 if (i0 + 32 < hmax) nxt = tab4[min(i0 + 32 + lane, hmax)];
-                if (i0 + 32 <= hmin) { WVA_SP2(false) } else { WVA_SP2(true) }
+                WVA_SP2()
             }
+#undef WVA_SP2_GROUP
 #undef WVA_SP2
         }
         WVA_PROF_T(13);

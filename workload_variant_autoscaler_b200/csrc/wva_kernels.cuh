@@ -405,15 +405,27 @@ __device__ __forceinline__ unsigned agg_inc(unsigned* counters, int key) {
     return base + __popc(peers & ((1u << lane) - 1u));
 }
 
-// SLO feasibility of an analysed cell (the build's grid semantics)
-__device__ __forceinline__ bool cell_feasible(const DevFleet& f, int s, int r, float rate, float rmax, const Metrics& m) {
-    const float slo_ttft = f.srv_slo_ttft[s], slo_itl = f.srv_slo_itl[s];
-    bool feas = (slo_ttft == 0.0f || m.ttft <= slo_ttft) && (slo_itl == 0.0f || m.avg_token_time <= slo_itl) &&
-                (r >= f.srv_min_replicas[s]);
-    if (f.srv_slo_tps[s] > 0.0f) {  // Size's stability margin (queueanalyzer.go:231-234)
-        const float lim = __fmul_rn(__fdiv_rn(rmax, 1000.0f), __fsub_rn(1.0f, 0.1f));
-        feas = feas && (__fdiv_rn(rate, 1000.0f) <= lim);
-    }
+// SLO feasibility of an analysed cell (the build's grid semantics).  The per-server
+// targets and the stability limit of the (pair, batch) are row constants; rate/1000 is the cell's lambda.
+struct FeasRow {
+    float slo_ttft, slo_itl, lim;  // lim = RateRange.Max/1000 * (1 - 0.1): Size's stability margin (queueanalyzer.go:231-234)
+    int min_replicas;
+    bool tps;
+};
+__device__ __forceinline__ float feas_lim(float rmax) { return __fmul_rn(__fdiv_rn(rmax, 1000.0f), __fsub_rn(1.0f, 0.1f)); }
+__device__ __forceinline__ FeasRow feas_row(const DevFleet& f, int s, float rmax) {
+    FeasRow fr;
+    fr.slo_ttft = f.srv_slo_ttft[s];
+    fr.slo_itl = f.srv_slo_itl[s];
+    fr.min_replicas = f.srv_min_replicas[s];
+    fr.tps = f.srv_slo_tps[s] > 0.0f;
+    fr.lim = feas_lim(rmax);
+    return fr;
+}
+__device__ __forceinline__ bool cell_feasible(const FeasRow& fr, int r, float lambda, const Metrics& m) {
+    bool feas = (fr.slo_ttft == 0.0f || m.ttft <= fr.slo_ttft) && (fr.slo_itl == 0.0f || m.avg_token_time <= fr.slo_itl) &&
+                (r >= fr.min_replicas);
+    if (fr.tps) feas = feas && (lambda <= fr.lim);
     return feas;
 }
 __device__ __forceinline__ void store_cell(const GridArgs& g, long long cell, int ok, int feas, const Metrics& m) {
@@ -509,47 +521,97 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
         const unsigned R = (unsigned)g.R, B = (unsigned)g.B, A = (unsigned)f.A;
         const unsigned row0 = (unsigned)(base / R), row1 = (unsigned)((base + n_here - 1) / R);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (unsigned row = row0 + warp; row <= row1; row += kSortThreads / 32) {
-            const unsigned sa = row / B;
-            const int bi = (int)(row - sa * B);
-            const int s = (int)(sa / A);
-            const long long toff = g.pair_tab_off[sa];
+        // feasible shared cells lower best_rank[(pair, replica level)]: a lane meets the same replica
+        // levels row after row, so it keeps the running minimum of its first two levels in registers
+        // and issues one atomic per pair instead of one per cell
+        unsigned cur_sa = 0xffffffffu;
+        int best0 = INT_MAX, best1 = INT_MAX;
+        auto flush_best = [&]() {
+            if (best0 != INT_MAX) atomicMin(&g.best_rank[(size_t)cur_sa * R + lane], best0);
+            if (best1 != INT_MAX) atomicMin(&g.best_rank[(size_t)cur_sa * R + lane + 32], best1);
+            best0 = best1 = INT_MAX;
+        };
+        // pair-level constants are re-read only when the walk crosses into the next pair; so are the
+        // lane's own row constants (its first two replica levels: rate, lambda, the row's shared chain)
+        struct LaneRow {
+            float4 rt;
+            double acc, sump;
+            int jl, rep;
+        };
+        LaneRow c0{}, c1{};
+        unsigned sa = (row0 + warp) / B;
+        int bi = (int)(row0 + warp - sa * B);
+        int s = 0, t = 0;
+        long long toff = -1;
+        QParams q{};
+        FeasRow fr{};
+        auto load_lane = [&](unsigned ri, LaneRow& c) {
+            if (ri >= R || toff < 0) return;
+            const size_t rowid = (size_t)sa * R + ri;
+            c.rt = g.rt[(unsigned)s * R + ri];
+            c.jl = g.row_j[rowid];
+            c.acc = g.row_acc[rowid];
+            c.sump = g.row_sump[rowid];
+            c.rep = g.replicas[ri];
+        };
+        for (unsigned row = row0 + warp; row <= row1; row += kSortThreads / 32, bi += kSortThreads / 32) {
+            while (bi >= (int)B) {
+                bi -= (int)B;
+                ++sa;
+            }
+            if (sa != cur_sa) {
+                flush_best();
+                cur_sa = sa;
+                s = (int)(sa / A);
+                toff = g.pair_tab_off[sa];
+                if (toff >= 0) {
+                    t = g.pair_tab_idx[sa];
+                    q = qparams_of(f, s, (int)(sa - (unsigned)s * A));
+                }
+                fr = feas_row(f, s, 0.0f);
+                load_lane(lane, c0);
+                load_lane(lane + 32, c1);
+            }
             const int b = g.batch[bi];
             const int K = b + b * f.ratio;
-            int t = 0;
             float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-            QParams q{};
-            if (toff >= 0) {
-                t = g.pair_tab_idx[sa];
-                pb = g.pb[(size_t)t * g.B + bi];
-                q = qparams_of(f, s, (int)(sa - (unsigned)s * A));
-            }
-            for (unsigned ri = lane; ri < R; ri += 32) {
+            if (toff >= 0) pb = g.pb[(size_t)t * g.B + bi];
+            fr.lim = feas_lim(pb.x);
+            const int rank = g.batch_rank[bi];
+            // one cell: (row, ri) with the lane's cached row constants
+            auto do_cell = [&](unsigned ri, const LaneRow& c, int slot) {
                 const long long cell = (long long)row * R + ri;
-                if (cell < base || cell >= base + n_here) continue;
+                if (cell < base || cell >= base + n_here) return;
                 int key = 255;
-                if (toff >= 0) {
-                    const float4 rt = g.rt[(unsigned)s * R + ri];
-                    if (!(rt.x <= 0.0f) && !(rt.x > pb.x) && K >= 2) {  // Analyze: queueanalyzer.go:135-143
-                        const size_t rowid = (size_t)sa * R + ri;
-                        const int jl = g.row_j[rowid];
-                        if (jl != INT_MAX && b >= jl + 2 && K < (1 << 23)) {
-                            // the whole solve is shared with the row: only the N-dependent tail is per cell
-                            ModelStats st;
-                            stats_from_row(g.row_acc[rowid], g.row_sump[rowid], b, rt.y, st);
-                            const Metrics m = metrics_from(q, b, st);
-                            const bool feas = cell_feasible(f, s, g.replicas[ri], rt.x, pb.x, m);
-                            store_cell(g, cell, 1, feas ? 1 : 0, m);
-                            if (feas) atomicMin(&g.best_rank[rowid], g.batch_rank[bi]);
-                        } else {
-                            key = length_class(estimate_len(g.tab + 4 * toff, g.ls + toff + t, b, K, rt.y, rt.z, pb.w, pb.y, pb.z));
+                if (toff >= 0 && !(c.rt.x <= 0.0f) && !(c.rt.x > pb.x) && K >= 2) {  // Analyze: queueanalyzer.go:135-143
+                    if (c.jl != INT_MAX && b >= c.jl + 2 && K < (1 << 23)) {
+                        // the whole solve is shared with the row: only the N-dependent tail is per cell
+                        ModelStats st;
+                        stats_from_row(c.acc, c.sump, b, c.rt.y, st);
+                        const Metrics m = metrics_from(q, b, st);
+                        const bool feas = cell_feasible(fr, c.rep, c.rt.y, m);
+                        store_cell(g, cell, 1, feas ? 1 : 0, m);
+                        if (feas) {
+                            if (slot == 0) best0 = min(best0, rank);
+                            else if (slot == 1) best1 = min(best1, rank);
+                            else atomicMin(&g.best_rank[(size_t)sa * R + ri], rank);
                         }
+                    } else {
+                        key = length_class(estimate_len(g.tab + 4 * toff, g.ls + toff + t, b, K, c.rt.y, c.rt.z, pb.w, pb.y, pb.z));
                     }
                 }
                 keys[cell - base] = (uint8_t)key;
-                seg_inc(hist, key);
+                if (key != 255) seg_inc(hist, key);  // class 255 (finished here / not analysable) needs no slot
+            };
+            if ((unsigned)lane < R) do_cell(lane, c0, 0);
+            if ((unsigned)lane + 32 < R) do_cell(lane + 32, c1, 1);
+            for (unsigned ri = lane + 64; ri < R; ri += 32) {
+                LaneRow c;
+                load_lane(ri, c);
+                do_cell(ri, c, 2);
             }
         }
+        flush_best();
     }
     __syncthreads();
     if (threadIdx.x < 32) {  // exclusive scan of the 256 class counts by one warp
@@ -570,6 +632,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
     const int n_active = (int)cursor[255];  // class 255 (not analysable) sorts last
     for (int k = threadIdx.x; k < n_here; k += kSortThreads) {
         const int key = keys[k];
+        if (key == 255) continue;
         const unsigned pos = seg_inc(cursor, key);
         g.order[base + pos] = (unsigned)(base + k);
         sorted_keys[pos] = (uint8_t)key;
@@ -665,7 +728,7 @@ __device__ __forceinline__ void grid_item(const GridArgs& g, unsigned w, unsigne
         } else {
             const QParams q = qparams_of(f, s, a);
             const Metrics m = metrics_from(q, N, st);
-            const bool feas = cell_feasible(f, s, r, rate, rmax, m);
+            const bool feas = cell_feasible(feas_row(f, s, rmax), r, lambda, m);
             store_cell(g, cell, 1, feas ? 1 : 0, m);
             if (feas) atomicMin(&g.best_rank[((size_t)s * f.A + a) * g.R + ri], g.batch_rank[bi]);
             if (g.dbg_cycles) {
@@ -745,7 +808,7 @@ __global__ void grid_fallback(GridArgs g, double* scratch, size_t slot_doubles, 
         }
         const QParams q = qparams_of(f, s, a);
         const Metrics m = metrics_from(q, b, st);
-        const bool feas = cell_feasible(f, s, r, rate, rmax, m);
+        const bool feas = cell_feasible(feas_row(f, s, rmax), r, __fdiv_rn(rate, 1000.0f), m);
         store_cell(g, cell, 1, feas ? 1 : 0, m);
         if (feas) atomicMin(&g.best_rank[((size_t)s * f.A + a) * g.R + ri], g.batch_rank[bi]);
     }
