@@ -582,11 +582,14 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
 // needs IEEE division, a chain that reaches the table end, window violations) just reports
 // "no sharing" and the cells go through grid_kernel as usual.
 // ---------------------------------------------------------------------------
-__device__ __noinline__ bool solve_row(const double* __restrict__ tab, int len, float lambda, double& acc_out,
-                                       double& sump_out, int& j_last) {
+// Inlined into its two call sites so that the shared-memory call compiles to LDS (grid_rows stages the
+// pair's table).  Both passes run 4 steps per window test where the exponent bounds allow it
+// (solve_shared_t's argument); lanes are independent rows, so there is no warp vote here.
+__device__ __forceinline__ bool solve_row(const double* __restrict__ tab, int len, float lambda, double& acc_out,
+                                          double& sump_out, int& j_last) {
     const double lam = (double)lambda;
     const int nh = len - 1;
-    Recip A;
+    Recip A, B;
     load_recip(tab, 0, A);
     if (!in_window(lam, kHiRateLo, kHiRateHi) || !in_window(A.b, kHiRateLo, kHiRateHi) || nh < 2) return false;
     double p = div_recip(lam, A);
@@ -595,10 +598,37 @@ __device__ __noinline__ bool solve_row(const double* __restrict__ tab, int len, 
     const unsigned thr_hi = (unsigned)__double2hiint(__dmul_rn(fmin(1.0, p1), 0x1p-78));
     const unsigned lo_eff = thr_hi > kHiPLo ? thr_hi : kHiPLo;
     const unsigned span_eff = kHiPHi - lo_eff;
+    // 4-step window: p may move by 2^(3 e_lo) .. 2^(3 e_hi) inside a block
+    unsigned blk_lo = 1, blk_span = 0;
+    {
+        const float smax = tab_prefix_max(tab, nh), smin = tab_suffix_min(tab, 0);
+        if (smin > 0.0f && smax >= smin) {
+            const int El = (int)(__float_as_uint(lambda) >> 23), Ex = (int)(__float_as_uint(smax) >> 23),
+                      En = (int)(__float_as_uint(smin) >> 23);
+            const int e_lo = El - Ex - 1, e_hi = El - En + 1;
+            const int lo_exp = -279 - 3 * (e_lo < 0 ? e_lo : 0), hi_exp = 600 - 3 * (e_hi > 0 ? e_hi : 0);
+            if (lo_exp < hi_exp && lo_exp > -1000 && hi_exp > -1000) {
+                const unsigned lo4 = WVA_HI(lo_exp), hi4 = WVA_HI(hi_exp);
+                blk_lo = lo4 > lo_eff ? lo4 : lo_eff;
+                blk_span = hi4 > blk_lo ? hi4 - blk_lo : 0;
+            }
+        }
+    }
     double sum = __dadd_rn(1.0, p);
     int n = 1;
-    Recip B;
     load_recip(tab, 1, A);  // triple of step n, loaded one step ahead of its use
+    // a chain that becomes negligible inside a block runs to the end of the block: those states add nothing,
+    // and the exit test below then sees an even smaller p at a later state of the same (decreasing) stretch
+    while (n + 4 < nh && WVA_FASTWIN(p, blk_lo, blk_span)) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            load_recip(tab, n + 1, B);
+            p = div_recip(__dmul_rn(p, lam), A);
+            sum = __dadd_rn(sum, p);
+            A = B;
+            ++n;
+        }
+    }
     while (n < nh && WVA_FASTWIN(p, lo_eff, span_eff)) {
         load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
         p = div_recip(__dmul_rn(p, lam), A);
@@ -619,7 +649,22 @@ __device__ __noinline__ bool solve_row(const double* __restrict__ tab, int len, 
     double acc = 0.0, sum_p = z.yh, di = 1.0;
     p = p1;
     load_recip(tab, 1, A);
-    for (int i = 1; i <= j_last; ++i) {
+    int i = 1;
+    // the block window's lower edge is >= 2^-279 / 2^(3 e_lo): all four states divide inside the window
+    while (i + 3 <= j_last && WVA_FASTWIN(p, blk_lo, blk_span)) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
+            const double pn = div_recip(p, z);
+            acc = __dadd_rn(acc, __dmul_rn(di, pn));
+            di = __dadd_rn(di, 1.0);
+            sum_p = __dadd_rn(sum_p, pn);
+            p = div_recip(__dmul_rn(p, lam), A);
+            A = B;
+            ++i;
+        }
+    }
+    for (; i <= j_last; ++i) {
         if (!WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) {
             if (p == 0.0) break;  // adds nothing (the cell's pass 2 stops here as well)
             return false;

@@ -471,7 +471,10 @@ __global__ void __launch_bounds__(128) grid_rows(GridArgs g) {
             const float thr = -78.0f + fminf(0.0f, rt.z - l2s0);
             const float Lend = (float)(g.Bmax - 1) * rt.z - ls_end;
             int jl = 0;
-            if (Lend < thr + 8.0f && solve_row(use, g.Bmax, rt.y, acc, sump, jl)) j = jl;
+            if (Lend < thr + 8.0f) {
+                const bool ok = staged ? solve_row(rows_tab, g.Bmax, rt.y, acc, sump, jl) : solve_row(tab, g.Bmax, rt.y, acc, sump, jl);
+                if (ok) j = jl;
+            }
         }
         g.row_j[row] = j;
         g.row_acc[row] = acc;
