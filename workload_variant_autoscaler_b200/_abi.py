@@ -136,7 +136,10 @@ class Allocs:
             setattr(self, name, np.zeros(n, dtype=dt))
 
     def as_c(self) -> AllocsC:
-        return AllocsC(*[ptr(getattr(self, name)) for name, _ in ALLOC_COLUMNS])
+        c = self.__dict__.get("_c")
+        if c is None:  # the columns are never re-attached: one struct per object
+            c = self.__dict__["_c"] = AllocsC(*[ptr(getattr(self, name)) for name, _ in ALLOC_COLUMNS])
+        return c
 
     def record(self, i: int) -> dict:
         return {name: getattr(self, name)[i].item() for name, _ in ALLOC_COLUMNS}

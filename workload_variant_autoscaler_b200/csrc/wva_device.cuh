@@ -402,6 +402,34 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         if (STASH > 0) {
             // states 1..min(STASH, j_end-1) come back from shared memory: no recurrence, no table loads
             const int i_st = (j_end - 1 < STASH) ? j_end - 1 : STASH;
+            // four states at a time while all four are inside the window and below N: the four
+            // normalisations are independent, only the accumulations are serial
+            {
+                const int i4 = i_st < N ? i_st : N;
+                while (i + 3 <= i4) {
+                    const double q0 = stash[(i - 1) * 32], q1 = stash[i * 32], q2 = stash[(i + 1) * 32], q3 = stash[(i + 2) * 32];
+                    if (!(WVA_FASTWIN(q0, kHiPLo, kHiPHi - kHiPLo) && WVA_FASTWIN(q1, kHiPLo, kHiPHi - kHiPLo) &&
+                          WVA_FASTWIN(q2, kHiPLo, kHiPHi - kHiPLo) && WVA_FASTWIN(q3, kHiPLo, kHiPHi - kHiPLo)))
+                        break;
+                    const double n0 = div_recip(q0, z), n1 = div_recip(q1, z), n2 = div_recip(q2, z), n3 = div_recip(q3, z);
+                    acc = __dadd_rn(acc, __dmul_rn(di, n0));
+                    di = __dadd_rn(di, 1.0);
+                    sum_p = __dadd_rn(sum_p, n0);
+                    acc = __dadd_rn(acc, __dmul_rn(di, n1));
+                    di = __dadd_rn(di, 1.0);
+                    sum_p = __dadd_rn(sum_p, n1);
+                    acc = __dadd_rn(acc, __dmul_rn(di, n2));
+                    di = __dadd_rn(di, 1.0);
+                    sum_p = __dadd_rn(sum_p, n2);
+                    acc = __dadd_rn(acc, __dmul_rn(di, n3));
+                    di = __dadd_rn(di, 1.0);
+                    sum_p = __dadd_rn(sum_p, n3);
+                    pn = n3;
+                    p = q3;
+                    acc_at_N = acc;
+                    i += 4;
+                }
+            }
 #pragma unroll 2
             for (; i <= i_st; ++i) {
                 p = stash[(i - 1) * 32];

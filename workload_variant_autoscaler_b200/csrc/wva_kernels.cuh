@@ -454,7 +454,6 @@ __global__ void __launch_bounds__(128) grid_rows(GridArgs g) {
         for (int i = threadIdx.x; i < 2 * g.Bmax; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const double* use = staged ? rows_tab : tab;
     float l2s0 = 0.f, ls_end = 0.f;
     if (toff >= 0) {
         l2s0 = log2f((float)tab[0]);
@@ -699,41 +698,54 @@ constexpr int kGkTabWin = 32;  // table entries staged per warp (solve_shared_t 
 constexpr int kGkLong = 1;     // long-item warps per SM (sub-partition 0)
 constexpr int kQLongN = 2 * kClasses + 1, kQLongCtr = kQLongN + 1, kQShortCtr = kQLongN + 2;  // in item_count[]
 
-__device__ __forceinline__ void grid_item(const GridArgs& g, unsigned w, unsigned lane, double* stash_warp, double* tbuf_warp) {
+// An item's operands (decoded cell, table, rates): prepared one item ahead, so that the dependent global
+// loads of the next item are in flight while the current one is being solved.
+struct ItemPrep {
+    unsigned w;
+    long long cell;
+    const double* tab;
+    int s, a, bi, ri, N, K, r;
+    float rmax, lambda;
+    bool valid;
+};
+__device__ __forceinline__ void item_prepare(const GridArgs& g, unsigned w, unsigned lane, ItemPrep& it) {
     const DevFleet& f = g.f;
     const unsigned long long item = g.items_sorted[w];
     // a partial item (the last of a sort chunk) is padded with copies of its first cell so that the
     // whole warp takes part in the staged table loads; the copies store nothing
-    const bool valid = lane < (unsigned)((item >> 32) & 0xff);
-    const unsigned idx = w * 32 + lane;
+    it.w = w;
+    it.valid = lane < (unsigned)((item >> 32) & 0xff);
+    it.cell = g.order[(unsigned)item + (it.valid ? lane : 0u)];
+    decode_cell(g, it.cell, it.s, it.a, it.bi, it.ri);
+    const int b = g.batch[it.bi];
+    it.r = g.replicas[it.ri];
+    const int pair = it.s * f.A + it.a;
+    it.tab = g.tab + 4 * g.pair_tab_off[pair];
+    it.N = b;
+    it.K = b + b * f.ratio;
+    it.rmax = g.pb[(size_t)g.pair_tab_idx[pair] * g.B + it.bi].x;
+    it.lambda = g.rt[it.s * g.R + it.ri].y;
+}
+__device__ __forceinline__ void item_run(const GridArgs& g, const ItemPrep& it, unsigned lane, double* stash_warp, double* tbuf_warp) {
+    const DevFleet& f = g.f;
+    const unsigned idx = it.w * 32 + lane;
     const long long t_start = g.dbg_cycles ? clock64() : 0;
     unsigned long long t_start_ns = 0;
     if (g.dbg_cycles) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start_ns));
-    WVA_PROF_T(9);
-    const long long cell = g.order[(unsigned)item + (valid ? lane : 0u)];
-    int s, a, bi, ri;
-    decode_cell(g, cell, s, a, bi, ri);
-    const int b = g.batch[bi], r = g.replicas[ri];
-    const int pair = s * f.A + a;
-    const double* tab = g.tab + 4 * g.pair_tab_off[pair];
-    const int N = b, K = b + b * f.ratio;
-    const float rmax = g.pb[(size_t)g.pair_tab_idx[pair] * g.B + bi].x;
-    const float4 rt = g.rt[s * g.R + ri];
-    const float rate = rt.x, lambda = rt.y;
     ModelStats st;
     WVA_PROF_T(10);
-    const int rc = solve_shared_t<kGridStash, 10, true>(tab, N, K, lambda, st, stash_warp + lane, tbuf_warp);
+    const int rc = solve_shared_t<kGridStash, 10, true>(it.tab, it.N, it.K, it.lambda, st, stash_warp + lane, tbuf_warp);
     WVA_PROF_T(11);
-    if (valid) {
+    if (it.valid) {
         if (rc != kSolveOk) {
             const int k = atomicAdd(g.fb_count, 1);
-            if (k < g.fb_cap) g.fb_cells[k] = cell;
+            if (k < g.fb_cap) g.fb_cells[k] = it.cell;
         } else {
-            const QParams q = qparams_of(f, s, a);
-            const Metrics m = metrics_from(q, N, st);
-            const bool feas = cell_feasible(feas_row(f, s, rmax), r, lambda, m);
-            store_cell(g, cell, 1, feas ? 1 : 0, m);
-            if (feas) atomicMin(&g.best_rank[((size_t)s * f.A + a) * g.R + ri], g.batch_rank[bi]);
+            const QParams q = qparams_of(f, it.s, it.a);
+            const Metrics m = metrics_from(q, it.N, st);
+            const bool feas = cell_feasible(feas_row(f, it.s, it.rmax), it.r, it.lambda, m);
+            store_cell(g, it.cell, 1, feas ? 1 : 0, m);
+            if (feas) atomicMin(&g.best_rank[((size_t)it.s * f.A + it.a) * g.R + it.ri], g.batch_rank[it.bi]);
             if (g.dbg_cycles) {
                 g.dbg_cycles[idx] = (unsigned)(clock64() - t_start);
                 if (lane < 3) {  // timeline: [0] start ns, [1] SM id, [2] end ns (low 32 bits of %globaltimer)
@@ -748,6 +760,12 @@ __device__ __forceinline__ void grid_item(const GridArgs& g, unsigned w, unsigne
     }
     __syncwarp();
     WVA_PROF_T(14);
+}
+__device__ __forceinline__ void grid_item(const GridArgs& g, unsigned w, unsigned lane, double* stash_warp, double* tbuf_warp) {
+    ItemPrep it;
+    WVA_PROF_T(9);
+    item_prepare(g, w, lane, it);
+    item_run(g, it, lane, stash_warp, tbuf_warp);
 }
 
 __global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
@@ -775,6 +793,9 @@ __global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
     } else if (sub0 && n_long && !long_warp && (int)(warp >> 2) >= g.long_per_sm + g.long_share) {
         asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
     }
+    // short queue.  (Pulling and preparing the next item before solving the current one was measured:
+    // the operands kept live across the solver call cost it registers and the 16-step loops slowed
+    // from 46 to 57 cycles per state.)
     for (;;) {
         unsigned w = 0;
         if (lane == 0) w = atomicAdd(g.item_count + kQShortCtr, 1u);

@@ -68,10 +68,15 @@ class Engine:
         self._check(self._L.wva_solve(self._h, C.byref(fc), C.byref(cc) if cc is not None else None, C.byref(wc)))
         return cand, win
 
-    def grid_solve(self, fleet: Fleet, grid: Grid, want_cells: bool = False):
-        """Full (server x acc x batch x replica) grid -> (cells | None, winners [S])."""
+    def grid_solve(self, fleet: Fleet, grid: Grid, want_cells: bool = False, out: Allocs | None = None):
+        """Full (server x acc x batch x replica) grid -> (cells | None, winners [S]).
+
+        ``out``: an ``Allocs`` of ``fleet.n_servers`` records to write the winners into (a reconcile
+        loop reuses one instead of allocating ten columns per call)."""
         n = fleet.n_servers * fleet.n_acc * int(grid.batch.size) * int(grid.replicas.size)
-        win = Allocs(fleet.n_servers)
+        if out is not None and out.n != fleet.n_servers:
+            raise ValueError("out must hold fleet.n_servers records")
+        win = out if out is not None else Allocs(fleet.n_servers)
         cells = None
         cc = None
         if want_cells:

@@ -116,11 +116,21 @@ class Fleet:
 
     def as_c(self) -> _abi.FleetC:
         """ctypes ``wva_fleet`` viewing this object's arrays (keep ``self`` alive)."""
-        p = _abi.ptr
-        c = _abi.FleetC()
+        # building ~45 ctypes pointers costs more than the rest of a small solve's host path: the struct is
+        # cached and reused while the very same array objects are still attached (in-place edits keep it valid)
+        names = self._F32 + self._I32 + self._U8
+        arrs = [getattr(self, n) for n in names]
+        cache = self.__dict__.get("_c_cache")
+        if cache is not None and all(a is b for a, b in zip(cache[0], arrs)):
+            c = cache[1]
+        else:
+            p = _abi.ptr
+            c = _abi.FleetC()
+            for n, a in zip(names, arrs):
+                setattr(c, n, p(a))
+            self.__dict__["_c_cache"] = (arrs, c)
+        c = _abi.FleetC.from_buffer_copy(c)  # callers may edit their struct; the cached one stays pristine
         c.n_acc, c.n_types, c.n_models, c.n_servers = self.n_acc, self.n_types, self.n_models, self.n_servers
-        for n in self._F32 + self._I32 + self._U8:
-            setattr(c, n, p(getattr(self, n)))
         c.unlimited = 1 if self.unlimited else 0
         c.delayed_best_effort = 1 if self.delayed_best_effort else 0
         c.saturation_policy = int(self.saturation_policy)
@@ -281,7 +291,12 @@ class Grid:
         self.replicas = _i32(self.replicas)
 
     def as_c(self) -> _abi.GridC:
-        return _abi.GridC(int(self.batch.size), _abi.ptr(self.batch), int(self.replicas.size), _abi.ptr(self.replicas))
+        cache = self.__dict__.get("_c_cache")
+        if cache is not None and cache[0] is self.batch and cache[1] is self.replicas:
+            return cache[2]
+        c = _abi.GridC(int(self.batch.size), _abi.ptr(self.batch), int(self.replicas.size), _abi.ptr(self.replicas))
+        self.__dict__["_c_cache"] = (self.batch, self.replicas, c)
+        return c
 
 
 # ----------------------------------------------------------------------------
