@@ -191,7 +191,8 @@ __device__ long long wva_prof[16];
 // the next window prefetched meanwhile.  Per-lane global loads two steps ahead of their use leave
 // most of the L2 latency exposed (every table entry is its own 32-byte sector): ~160 cycles per head
 // step on an idle SM and 300+ on a busy one, against ~55 from the staged window (tools/head_bench.cu).
-template <int STASH, int PF = 10, bool STAGED = false>
+// REV: pairs of checked steps a lane set takes on the per-step path before it returns to the block vote (0 = never returns)
+template <int STASH, int PF = 10, bool STAGED = false, int REV = 1>
 __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st,
                                            double* __restrict__ stash, double* __restrict__ tbuf = nullptr) {
     const unsigned warp_mask = __activemask();
@@ -351,14 +352,14 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             // Per-step phase: at most two checked steps, then back to the vote — the lane that failed the
             // block vote (near its end, or p about to leave the window) is usually gone by then and the
             // others must not stay on this slower path for the rest of their chain.
-            {
+            for (int rv = 0; REV == 0 || rv < REV; ++rv) {
                 if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) goto p1_slow;
                 if (n < nh) prefetch_l1(tab + 4 * (n + PF));
                 WVA_P1_STEP(A)
                 if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) goto p1_slow;
                 WVA_P1_STEP(B)
-                continue;
             }
+            continue;
 #undef WVA_P1_STEP
         p1_slow:
             if (n >= n_stop) break;
@@ -554,14 +555,14 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 }
                 break;
             }
-            {  // per-step phase: two checked steps, then back to the vote (see pass 1)
+            for (int rv = 0; REV == 0 || rv < REV; ++rv) {  // per-step phase (see pass 1)
                 if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) goto p2_slow;
                 if (i < nh) prefetch_l1(tab + 4 * (i + PF));
                 WVA_P2_STEP(A)
                 if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) goto p2_slow;
                 WVA_P2_STEP(B)
-                continue;
             }
+            continue;
 #undef WVA_P2_STEP
         p2_slow:
             if (i >= j_end) break;
@@ -728,7 +729,9 @@ __device__ __forceinline__ int solve_shared(const double* __restrict__ tab, int 
 }
 // Per-lane private tables (size path): every lane streams its own table, so prefetch much further ahead.
 __device__ __forceinline__ int solve_private(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st) {
-    return solve_shared_t<0, 48>(tab, N, K, lambda, st, nullptr);
+    // lanes with private tables rarely agree on a block again once one of them left it: stay on the
+    // per-step path (REV = 0; measured on config 4: 27.6 ms against 31.0 ms with REV = 1)
+    return solve_shared_t<0, 48, false, 0>(tab, N, K, lambda, st, nullptr);
 }
 
 // Stored-vector fallback: a literal restatement of computeProbabilities /
