@@ -54,7 +54,9 @@ def parse_args():
 
 def workload(rank: int):
     from workload_variant_autoscaler_b200 import config2_grid, synth_fleet
-    fleet = synth_fleet(N_MODELS, N_ACC, seed=42 + rank)
+    # weak scaling = fixed work per GPU: every rank draws its 100 models from the same seeded stream (the
+    # grid kernel's time varies by +-30 % with the draw, which would otherwise be measured as 'scaling')
+    fleet = synth_fleet(N_MODELS, N_ACC, seed=42)
     grid = config2_grid(N_BATCH, N_REPLICAS)
     return fleet, grid
 
@@ -67,7 +69,7 @@ def config_dict(n_gpus: int) -> dict:
         "models_per_gpu": N_MODELS, "accelerators": N_ACC, "batch_sizes": N_BATCH, "replica_levels": N_REPLICAS,
         "mean_states_per_cell": 11 * (N_BATCH + 1) / 2,
         "seed": 42, "l2_flush_between_steps": True,
-        "parallelism": f"dp{n_gpus} over models, one NCCL all-gather of winners" if n_gpus > 1 else "single GPU",
+        "parallelism": f"dp{n_gpus} over models, one all-gather of the winner blocks per step" if n_gpus > 1 else "single GPU",
         "cell_table_materialised": False,
     }
 
@@ -241,10 +243,49 @@ def run_ours(args):
 
     eng.upload(fleet)  # inputs resident in HBM before the timed region
 
+    # N > 1: one all-gather of the 4 KB winner blocks per step.  Default: NCCL.  WVA_BENCH_PEER=1 selects the
+    # library's own exchange kernel (wva_xchg_publish: NVLink stores into every peer's buffer + epoch flags, one
+    # launch); measured at N = 2 it is as fast as NCCL's low-latency path (0.405 vs 0.403 ms/step), so the
+    # proven collective stays the default.
+    xchg, exchange = None, "none (single GPU)"
+    if world > 1:
+        exchange = "nccl all_gather_into_tensor"
+        try:
+            if not os.environ.get("WVA_BENCH_PEER"):
+                raise RuntimeError("not requested")
+            from workload_variant_autoscaler_b200.parallel import PeerExchange
+            xchg = PeerExchange(eng, win_local.numel() * 4)
+            exchange = "peer-memory kernel (wva_xchg_publish): NVLink stores + epoch flags, one launch"
+        except Exception as exc:  # noqa: BLE001 - report and use the library collective
+            xchg = None
+            if os.environ.get("WVA_BENCH_PEER"):
+                exchange += f" (peer exchange unavailable: {exc})"
+        ok = torch.tensor([1 if xchg is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            xchg = None
+
     def step_device():
         eng.grid_solve_device(grid, cols)
         if world > 1:
+            if xchg is not None:
+                xchg.publish(base)
+            else:
+                dist.all_gather_into_tensor(win_all, win_local)
+
+    if xchg is not None:
+        # one checked step: the peer exchange must deliver exactly what the library collective delivers
+        class _Raw:  # zero-copy view of the gathered device buffer
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+        with torch.cuda.stream(ext):
+            eng.grid_solve_device(grid, cols)
+            gptr, stride = xchg.publish(base)
             dist.all_gather_into_tensor(win_all, win_local)
+        torch.cuda.synchronize()
+        got = torch.as_tensor(_Raw(gptr, world * stride // 4), device=dev).view(world, stride // 4)[:, : win_local.numel()]
+        if xchg.error() or not torch.equal(got.reshape(-1), win_all):
+            raise SystemExit("peer exchange delivered a different gathered block than NCCL")
 
     def timed_steps(k):
         """K steps, each timed with CUDA events on the launching stream; L2 flushed in between."""
@@ -337,7 +378,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(world),
+            "config": dict(config_dict(world), exchange=exchange),
             "e2e": {"value": n_cells * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h),
                     "note": "wva_grid_solve through the C ABI with host buffers: H2D of the fleet (staged through the "

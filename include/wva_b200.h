@@ -263,6 +263,24 @@ int64_t wva_launch_count(const wva_handle *h);
 float wva_last_kernel_ms(const wva_handle *h);
 float wva_last_device_ms(const wva_handle *h);
 
+/* --- multi-GPU: all-gather of the per-rank winner block over peer memory --------------------
+ * One process per GPU on one node.  Replaces the collective the reference does not have (its optimizer
+ * is single-process): each rank writes its block straight into every peer's gathered
+ * buffer over NVLink and waits for the peers' blocks, in ONE kernel on the handle's stream.
+ *   wva_xchg_create   allocate this rank's gathered buffer, return its 64-byte CUDA IPC handle
+ *   wva_xchg_open     register the IPC handle of rank `peer_rank` (exchange the handles with any
+ *                     host-side transport, e.g. torch.distributed all_gather_object); call for every rank
+ *   wva_xchg_publish  enqueue the exchange of `src_block` (device memory, block_bytes); *gathered is the
+ *                     device address of this step's [world][*slot_stride] byte buffer, valid once the
+ *                     stream has passed the call (double-buffered by step parity)
+ *   wva_xchg_error    after a synchronize: 1 if a peer never arrived (the kernel gives up after ~2 s)
+ */
+int wva_xchg_create(wva_handle *h, int world, int rank, size_t block_bytes, void *ipc_handle_out);
+int wva_xchg_open(wva_handle *h, int peer_rank, const void *ipc_handle);
+int wva_xchg_publish(wva_handle *h, const void *src_block, void **gathered, size_t *slot_stride);
+int wva_xchg_error(wva_handle *h);
+int wva_xchg_destroy(wva_handle *h);
+
 #ifdef __cplusplus
 }
 #endif

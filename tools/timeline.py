@@ -9,7 +9,8 @@ from workload_variant_autoscaler_b200 import Engine, config2_grid, synth_fleet  
 
 e = Engine(0)
 L = e._L
-f = synth_fleet(100, 4, seed=42)
+SEED = int(sys.argv[1]) if len(sys.argv) > 1 else 42
+f = synth_fleet(100, 4, seed=SEED)
 g = config2_grid()
 L.wva_dbg_enable_cycles(e._h, 1)
 for _ in range(6):
@@ -19,7 +20,7 @@ cyc = np.zeros(n, np.uint32)
 tl = np.zeros(n, np.uint32)
 L.wva_dbg_read_cycles.restype = C.c_longlong
 got = L.wva_dbg_read_cycles(e._h, cyc.ctypes.data_as(C.c_void_p), tl.ctypes.data_as(C.c_void_p), C.c_longlong(n))
-print("kernel ms", e.last_kernel_ms)
+print("seed", SEED, "kernel ms", e.last_kernel_ms)
 nw = got // 32
 cw = cyc[: nw * 32].reshape(nw, 32).max(axis=1)
 t = tl[: nw * 32].reshape(nw, 32)
@@ -53,3 +54,7 @@ for lo in (0, 50, 100, 150, 200, 300, 400, 500, 600, 800, 1000, 1500, 2000, 3000
     sel = (idx >= lo) & (idx < lo + 50)
     if sel.any():
         print("warps %6d..: start %.1f us dur %.1f us (max %.1f) cycles/lane mean %.0f" % (lo, start[sel].mean() / 1e3, dur[sel].mean() / 1e3, dur[sel].max() / 1e3, cw[sel].mean()))
+
+for thr in (400e3, 300e3, 200e3, 150e3, 100e3, 50e3):
+    print("items with lane cycles > %dk: %d" % (thr / 1e3, int((cw > thr).sum())))
+print("sum of item durations (warp-us): %.0f   / (148 SMs x 13 warps) = %.1f us" % (dur.sum() / 1e3, dur.sum() / 1e3 / (148 * 13)))

@@ -144,6 +144,17 @@ struct wva_handle {
     DevBuf d_grid_lists, d_pair_tab, d_tab_pair, d_tab_off, d_tab_len, d_tab, d_ls, d_sort, d_best, d_pb, d_rows;
     // shared
     DevBuf d_cand_block, d_win_block, d_ctrl, d_fb_list, d_scratch, d_cells, d_sweep, d_dbg;
+    // peer exchange of the winner block (multi-GPU, one process per GPU on one node)
+    struct Xchg {
+        int world = 0, rank = 0;
+        size_t block_bytes = 0, slot_stride = 0;   // one gathered buffer = world * slot_stride bytes
+        char* local = nullptr;                     // [2 parities][world slots] + flags, cudaMalloc'ed here
+        size_t local_bytes = 0, flags_off = 0;
+        std::vector<char*> peer;                   // base pointers of every rank's buffer (peer[rank] == local)
+        char** d_peer = nullptr;
+        unsigned long long epoch = 0;
+        int* d_err = nullptr;
+    } xchg;
     bool dbg_cycles = false;
     size_t dbg_n = 0;
     PinBuf out_stage;
@@ -1182,6 +1193,125 @@ void wva_destroy(wva_handle* h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
+
+// ---------------------------------------------------------------------------
+// Winner-block all-gather over peer memory (NVLink / NVSwitch), fused into ONE kernel per step:
+// CTA d copies this rank's block into rank d's gathered buffer (slot = this rank) with plain peer
+// stores, publishes the step's epoch in rank d's flag word for this rank (release, system scope),
+// then waits until rank d's block has arrived HERE.  When the kernel retires every slot of the
+// local gathered buffer holds this step's blocks.  Two buffer parities: a fast rank may already
+// publish step e+1 while a slow one still reads step e.  The payload is 40 B per server, so the
+// exchange is latency: two NVLink hops instead of a library collective's launch + protocol.
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) xchg_publish(const char* __restrict__ src, size_t bytes, char* const* __restrict__ peers,
+                                                    int world, int rank, size_t slot_stride, size_t flags_off,
+                                                    unsigned long long epoch, int* err) {
+    const int d = blockIdx.x;
+    const size_t parity_off = (size_t)(epoch & 1ull) * (size_t)world * slot_stride;
+    char* dst = peers[d] + parity_off + (size_t)rank * slot_stride;
+    const size_t n16 = bytes / 16;
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) ((int4*)dst)[i] = ((const int4*)src)[i];
+    for (size_t i = 16 * n16 + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // my flag word in rank d's memory: flags[src rank]
+        volatile unsigned long long* theirs = (volatile unsigned long long*)(peers[d] + flags_off) + rank;
+        *theirs = epoch;
+        __threadfence_system();
+        // wait for rank d's block of this epoch in MY memory
+        volatile unsigned long long* mine = (volatile unsigned long long*)(peers[rank] + flags_off) + d;
+        const long long t0 = clock64();
+        while (*mine < epoch) {
+            if (clock64() - t0 > (4ll << 30)) {  // ~2 s: a peer is gone; report instead of hanging the GPU
+                *err = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+}
+}  // namespace
+
+extern "C" {
+int wva_xchg_create(wva_handle* h, int world, int rank, size_t block_bytes, void* ipc_handle_out /* 64 bytes */) {
+    if (!h || world < 1 || rank < 0 || rank >= world || !ipc_handle_out) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    auto& x = h->xchg;
+    x.world = world;
+    x.rank = rank;
+    x.block_bytes = block_bytes;
+    x.slot_stride = (block_bytes + 255) / 256 * 256;
+    x.flags_off = 2 * (size_t)world * x.slot_stride;
+    x.local_bytes = x.flags_off + 8 * (size_t)world + 256;
+    CK(cudaMalloc((void**)&x.local, x.local_bytes));  // its own allocation: IPC exports whole allocations
+    CK(cudaMemset(x.local, 0, x.local_bytes));
+    CK(cudaMalloc((void**)&x.d_peer, sizeof(char*) * world));
+    CK(cudaMalloc((void**)&x.d_err, sizeof(int)));
+    CK(cudaMemset(x.d_err, 0, sizeof(int)));
+    x.peer.assign(world, nullptr);
+    x.peer[rank] = x.local;
+    x.epoch = 0;
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, x.local));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &hd, sizeof(hd));
+    return WVA_OK;
+}
+int wva_xchg_open(wva_handle* h, int peer_rank, const void* ipc_handle) {
+    if (!h || !ipc_handle || peer_rank < 0 || peer_rank >= h->xchg.world) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    auto& x = h->xchg;
+    if (peer_rank != x.rank) {
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, ipc_handle, sizeof(hd));
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        x.peer[peer_rank] = (char*)p;
+    }
+    bool all = true;
+    for (char* p : x.peer) all = all && p != nullptr;
+    if (all) CK(cudaMemcpy(x.d_peer, x.peer.data(), sizeof(char*) * x.world, cudaMemcpyHostToDevice));
+    return WVA_OK;
+}
+// Enqueue the exchange of `src_block` (device memory, block_bytes) on the handle's stream; returns the
+// device address of the gathered buffer of this step ([world][slot_stride] bytes) in *gathered.
+int wva_xchg_publish(wva_handle* h, const void* src_block, void** gathered, size_t* slot_stride) {
+    if (!h || !src_block || h->xchg.world < 1 || !h->xchg.d_peer) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    auto& x = h->xchg;
+    for (char* p : x.peer)
+        if (!p) return h->fail(WVA_ERR_STATE, "wva_xchg_publish: not every peer buffer is open");
+    ++x.epoch;
+    xchg_publish<<<x.world, 256, 0, h->stream>>>((const char*)src_block, x.block_bytes, x.d_peer, x.world, x.rank, x.slot_stride,
+                                                 x.flags_off, x.epoch, x.d_err);
+    h->launches++;
+    if (gathered) *gathered = x.local + (size_t)(x.epoch & 1ull) * (size_t)x.world * x.slot_stride;
+    if (slot_stride) *slot_stride = x.slot_stride;
+    CK(cudaGetLastError());
+    return WVA_OK;
+}
+int wva_xchg_error(wva_handle* h) {  // after a synchronize: 1 = a peer never arrived
+    if (!h || !h->xchg.d_err) return 0;
+    int e = 0;
+    cudaMemcpy(&e, h->xchg.d_err, sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
+}
+int wva_xchg_destroy(wva_handle* h) {
+    if (!h) return WVA_ERR_BAD_ARG;
+    auto& x = h->xchg;
+    cudaSetDevice(h->device);
+    for (int r = 0; r < (int)x.peer.size(); ++r)
+        if (r != x.rank && x.peer[r]) cudaIpcCloseMemHandle(x.peer[r]);
+    if (x.local) cudaFree(x.local);
+    if (x.d_peer) cudaFree(x.d_peer);
+    if (x.d_err) cudaFree(x.d_err);
+    x = wva_handle::Xchg();
+    return WVA_OK;
+}
+}  // extern "C"
 
 void* wva_stream(wva_handle* h) { return h ? (void*)h->stream : nullptr; }
 

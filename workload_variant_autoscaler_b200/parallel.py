@@ -66,3 +66,43 @@ def torch_all_gather(group=None, device=None):
         return out.cpu().numpy().reshape((world,) + tuple(block.shape))
 
     return _ag
+
+
+class PeerExchange:
+    """All-gather of a fixed-size device block over peer memory (``wva_xchg_*``, include/wva_b200.h).
+
+    One process per GPU on one node.  The 64-byte CUDA IPC handles of the ranks' gathered buffers are
+    exchanged once over ``torch.distributed`` (host side); after that every step is ONE kernel on the
+    engine's stream that writes this rank's block into all peers over NVLink and waits for theirs —
+    no library collective, no extra stream hand-over.
+    """
+
+    def __init__(self, engine, block_bytes: int, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        self._e, self._L, self._C = engine, engine._L, C
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.block_bytes = int(block_bytes)
+        mine = C.create_string_buffer(64)
+        engine._check(self._L.wva_xchg_create(engine._h, self.world, self.rank, self.block_bytes, mine))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine.raw), group=group)
+        for r, hb in enumerate(handles):
+            engine._check(self._L.wva_xchg_open(engine._h, r, C.create_string_buffer(hb, 64)))
+        dist.barrier(group)  # every rank has mapped every buffer before the first publish
+
+    def publish(self, src_device_ptr: int):
+        """Enqueue the exchange of the block at ``src_device_ptr``; returns (device address of the gathered
+        [world][slot_stride] buffer of this step, slot_stride)."""
+        C = self._C
+        out, stride = C.c_void_p(), C.c_size_t()
+        self._e._check(self._L.wva_xchg_publish(self._e._h, C.c_void_p(src_device_ptr), C.byref(out), C.byref(stride)))
+        return int(out.value), int(stride.value)
+
+    def error(self) -> int:
+        return int(self._L.wva_xchg_error(self._e._h))
+
+    def close(self):
+        self._L.wva_xchg_destroy(self._e._h)
