@@ -156,6 +156,7 @@ struct wva_handle {
         int* d_err = nullptr;
     } xchg;
     bool dbg_cycles = false;
+    const unsigned* dbg_plan = nullptr;
     size_t dbg_n = 0;
     PinBuf out_stage;
 
@@ -767,13 +768,14 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     const size_t nc = std::max<size_t>(plan->n_cells, 1);
     // sort workspace: order u32 [n_cells] | items u64 | items_sorted u64 | item counter
     const size_t max_items = (nc + 31) / 32 + (size_t)std::max(plan->n_blocks, 1);
-    const size_t ws = align_up(4 * nc) + 2 * align_up(8 * max_items) + 4 * (2 * kClasses + 8);
+    const size_t ws = align_up(4 * nc) + 2 * align_up(8 * max_items) + 4 * (2 * kClasses + 32);
     CK(h->d_sort.ensure(ws));
     char* w = (char*)h->d_sort.p;
     g.order = (unsigned*)w;
     g.items = (unsigned long long*)(w + align_up(4 * nc));
     g.items_sorted = (unsigned long long*)(w + align_up(4 * nc) + align_up(8 * max_items));
     g.item_count = (unsigned*)(w + align_up(4 * nc) + 2 * align_up(8 * max_items));
+    h->dbg_plan = g.item_count + 2 * kClasses + 1;
     const size_t n_best = std::max<size_t>((size_t)S * A * R, 1);
     CK(h->d_best.ensure(sizeof(int) * n_best));
     g.best_rank = (int*)h->d_best.p;
@@ -789,13 +791,14 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     {
         // grid_kernel's long queue: items of at least ~min_len states, at most long_per_sm per SM
         int long_per_sm = kGkLong, min_len = 1024;
-        if (const char* e = getenv("WVA_GRID_LONG")) long_per_sm = std::min(std::max(atoi(e), 0), kGkWarps / 4);
+        if (const char* e = getenv("WVA_GRID_LONG")) long_per_sm = std::min(std::max(atoi(e), -1), kGkWarps / 4);
         if (const char* e = getenv("WVA_GRID_LONG_MINLEN")) min_len = std::max(atoi(e), 2);
         g.long_per_sm = long_per_sm;
         g.long_share = 0;
         if (const char* e = getenv("WVA_GRID_SHARE")) g.long_share = std::max(atoi(e), 0);
         g.long_cls = 254 - std::min(std::max((int)(log2f((float)min_len) * 12.0f), 0), 254);
-        g.long_cap = (unsigned)(long_per_sm * h->sm_count);
+        g.long_cap = (unsigned)(std::max(long_per_sm, 0) * h->sm_count);
+        g.n_ctas = h->sm_count;
     }
     if (h->dbg_cycles) {
         CK(h->d_dbg.ensure(sizeof(unsigned) * nc * 2));
@@ -820,7 +823,7 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
     if (plan.n_cells > 0) {
         CK(cudaMemsetAsync(g.cells.flags, 0, plan.n_cells, h->stream));
         fill_int<<<(unsigned)((n_best + 255) / 256), 256, 0, h->stream>>>(g.best_rank, n_best, INT_MAX);
-        CK(cudaMemsetAsync(g.item_count, 0, sizeof(unsigned) * (2 * kClasses + 8), h->stream));
+        CK(cudaMemsetAsync(g.item_count, 0, sizeof(unsigned) * (2 * kClasses + 32), h->stream));
         {
             const int rows_threads = g.R >= 128 ? 128 : (g.R > 32 ? 64 : 32);
             const size_t rows_smem = g.Bmax <= kRowsSmemEntries ? (size_t)g.Bmax * 32 : 0;
@@ -1649,6 +1652,10 @@ int wva_dbg_prof(long long* out, int reset) {
     return (int)cudaMemcpyFromSymbol(out, wva::wva_prof, sizeof(long long) * 16);
 }
 #endif
+int wva_dbg_read_plan(wva_handle* h, unsigned* out32) {  // grid_items_scan's queue plan: item_count[2*kClasses+1 ..+31]
+    if (!h || !h->d_sort.p || !h->dbg_plan) return -1;
+    return (int)cudaMemcpy(out32, h->dbg_plan, sizeof(unsigned) * 31, cudaMemcpyDeviceToHost);
+}
 int wva_dbg_enable_cycles(wva_handle* h, int on) {
     if (!h) return WVA_ERR_BAD_ARG;
     h->dbg_cycles = on != 0;

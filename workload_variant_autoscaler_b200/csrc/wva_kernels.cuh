@@ -344,7 +344,8 @@ struct GridArgs {
     int* fb_count;           // cells that need the stored-vector fallback
     long long* fb_cells;
     int fb_cap;
-    int long_per_sm;         // grid_kernel: warps per SM (sub-partition 0) that pull the long queue
+    int long_per_sm;         // grid_kernel: long items per sub-partition 0 (< 0: chosen per launch by grid_items_scan)
+    int n_ctas;              // CTAs of grid_kernel (= SMs)
     int long_share;          // ... and how many other warps of that sub-partition may pull short items meanwhile
     int long_cls;            // items of class <= long_cls are "long" ...
     unsigned long_cap;       // ... up to this many (long_per_sm x CTAs)
@@ -654,22 +655,89 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
 
 // Global order of the warp items by class (longest first): class cursors from the global
 // histogram, then a multi-CTA scatter with warp-aggregated atomics.
+// grid_kernel's CTA shape (the kernel is further down; grid_items_scan plans its queues)
+constexpr int kGkWarps = 16;    // 4 per sub-partition; 128 registers per thread keep the two FP64 chains of pass 2 apart
+constexpr int kGkThreads = kGkWarps * 32;
+constexpr int kGkTabWin = 32;  // table entries staged per warp (solve_shared_t STAGED)
+constexpr int kGkLong = -1;    // long-item warps per CTA: automatic     // long-item warps per SM (sub-partition 0)
+// Model of grid_kernel's launch time, calibrated on BASELINE config 2 with seeds 42..49 (tools/seed_times.py
+// prints the plan next to the measured time): class c holds chains of 2^((254-c)/12) states;
+//   item_us  what an item costs the short queue: ~0.099 us per state (two passes, ~96 cycles per state
+//            and pass next to three other warps of the sub-partition, stalls included) + 7 us fixed;
+//   long_us  an item that has its sub-partition to itself: 0.0564 us per state + 4 us.
+__device__ __forceinline__ float class_len(int c) { return exp2f((float)(254 - c) * (1.0f / 12.0f)); }
+__device__ __forceinline__ float item_us(int c) { return 0.0987f * class_len(c) + 7.0f; }
+__device__ __forceinline__ float long_us(int c) { return 0.0564f * class_len(c) + 4.0f; }
 __global__ void __launch_bounds__(256) grid_items_scan(GridArgs g) {
-    __shared__ unsigned tot[kClasses];
-    tot[threadIdx.x] = g.item_count[1 + threadIdx.x];
+    __shared__ unsigned cnt[kClasses + 1];  // exclusive prefix of the class counts (cnt[kClasses] = all items)
+    __shared__ float wrk[kClasses + 1];     // exclusive prefix of the classes' work (warp-microseconds)
+    __shared__ unsigned s_cnt[kClasses];
+    __shared__ float s_wrk[kClasses];
+    const int c = threadIdx.x;
+    const unsigned mine = g.item_count[1 + c];
+    const float us = item_us(c);
+    s_cnt[c] = mine;
+    s_wrk[c] = c < 255 ? (float)mine * us : 0.0f;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned acc = 0, n_long = 0;
-        for (int c = 0; c < kClasses; ++c) {
-            g.item_count[1 + kClasses + c] = acc;
-            acc += tot[c];
-            if (c <= g.long_cls) n_long = acc;  // items at least that long
+    for (int d = 1; d < kClasses; d <<= 1) {  // inclusive Hillis-Steele scans
+        const unsigned a = c >= d ? s_cnt[c - d] : 0u;
+        const float w = c >= d ? s_wrk[c - d] : 0.0f;
+        __syncthreads();
+        s_cnt[c] += a;
+        s_wrk[c] += w;
+        __syncthreads();
+    }
+    cnt[c + 1] = s_cnt[c];
+    wrk[c + 1] = s_wrk[c];
+    if (c == 0) {
+        cnt[0] = 0;
+        wrk[0] = 0.0f;
+    }
+    g.item_count[1 + kClasses + c] = s_cnt[c] - mine;  // class cursors for grid_items_scatter
+    __syncthreads();
+    // grid_kernel's queues: the long queue is the head of the sorted list, the short queue the rest.
+    // How many long items share a sub-partition (L) is chosen per launch from a two-term model of the
+    // launch time, max(longest item at L per sub-partition, short-queue work / worker warps): more per
+    // sub-partition slows the long chains (x1.15 alone, x1.31, x1.58, x2.0 measured for L = 1..4) but
+    // takes fewer sub-partitions away from the short queue.  Thread l evaluates L = l + 1.
+    __shared__ float t_of[kGkWarps / 4];
+    const int long_cls = g.long_cls < 0 ? -1 : (g.long_cls > 254 ? 254 : g.long_cls);
+    const unsigned n_long_all = long_cls >= 0 ? cnt[long_cls + 1] : 0u;
+    if (c < kGkWarps / 4) {
+        const float slow[4] = {1.155f, 1.31f, 1.585f, 2.0f};
+        const int l = c + 1;
+        const unsigned nl = min(n_long_all, (unsigned)(l * g.n_ctas));
+        const unsigned ctas = (nl + l - 1) / l;
+        // work of the nl longest items: whole classes below the class that holds item nl, part of that one
+        int lo = 0, hi = kClasses;  // first class k with cnt[k + 1] >= nl
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cnt[mid + 1] >= nl) hi = mid; else lo = mid + 1;
         }
-        // grid_kernel's queues: the long queue is the head of the sorted list, the short queue the rest
-        n_long = min(n_long, g.long_cap);
+        const int k = lo < kClasses ? lo : kClasses - 1;
+        const float long_work = wrk[k] + (float)(nl - cnt[k]) * item_us(k);
+        int c_max = 0;
+        while (c_max < kClasses - 1 && cnt[c_max + 1] == 0) ++c_max;  // longest class present
+        const float workers = (float)(kGkWarps * g.n_ctas) - 4.0f * (float)ctas;
+        const float t_short = (wrk[kClasses] - long_work) / fmaxf(workers, 1.0f);
+        const float t_long = nl ? slow[c] * long_us(c_max) : 0.0f;
+        t_of[c] = fmaxf(t_short, t_long);
+        g.item_count[2 * kClasses + 8 + 2 * c] = __float_as_uint(t_short);  // diagnostics (wva_dbg_read_plan)
+        g.item_count[2 * kClasses + 9 + 2 * c] = __float_as_uint(t_long);
+    }
+    __syncthreads();
+    if (c == 0) {
+        int L = g.long_per_sm;
+        if (L < 0) {
+            L = 1;
+            for (int l = 2; l <= kGkWarps / 4; ++l)
+                if (t_of[l - 1] < t_of[L - 1]) L = l;
+        }
+        const unsigned n_long = min(n_long_all, (unsigned)(L * g.n_ctas));
         g.item_count[2 * kClasses + 1] = n_long;
         g.item_count[2 * kClasses + 2] = 0;
         g.item_count[2 * kClasses + 3] = n_long;
+        g.item_count[2 * kClasses + 4] = (unsigned)L;
     }
 }
 __global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
@@ -692,10 +760,6 @@ __global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
 //   * the SHORT queue = everything else, longest first, pulled by all other warps (and by the
 //     sub-partition-0 warps once the CTA's long work is finished).
 // ---------------------------------------------------------------------------
-constexpr int kGkWarps = 16;    // 4 per sub-partition; 128 registers per thread keep the two FP64 chains of pass 2 apart
-constexpr int kGkThreads = kGkWarps * 32;
-constexpr int kGkTabWin = 32;  // table entries staged per warp (solve_shared_t STAGED)
-constexpr int kGkLong = 1;     // long-item warps per SM (sub-partition 0)
 constexpr int kQLongN = 2 * kClasses + 1, kQLongCtr = kQLongN + 1, kQShortCtr = kQLongN + 2;  // in item_count[]
 
 // An item's operands (decoded cell, table, rates): prepared one item ahead, so that the dependent global
@@ -775,12 +839,17 @@ __global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
     double* tbuf_warp = stash_warp + kGridStash * 32;  // 32 table entries of 4 doubles
     const unsigned n_items = g.item_count[0], n_long = g.item_count[kQLongN];
     const bool sub0 = (warp & 3) == 0;
-    const bool long_warp = sub0 && (warp >> 2) < (unsigned)g.long_per_sm;
+    // the long items are spread over as few CTAs as possible (long_per_sm per CTA): the other CTAs keep all
+    // four sub-partitions for the short queue
+    const int per = (int)g.item_count[kQLongN + 3];  // long items per sub-partition, chosen by grid_items_scan
+    const int long_ctas = per > 0 ? (int)((n_long + per - 1) / per) : 0;
+    const int my_long = (int)blockIdx.x < long_ctas ? per : 0;
+    const bool long_warp = sub0 && (int)(warp >> 2) < my_long;
     // sub-partition 0: long_per_sm warps pull the long queue, long_share more may pull short items next
     // to them, the rest wait on named barrier 1 (blocked in hardware: no issue slots) until the long warps
     // of this CTA have drained the long queue
-    const int n_parked = kGkWarps / 4 - g.long_per_sm - g.long_share;
-    const int bar_threads = 32 * (g.long_per_sm + (n_parked > 0 ? n_parked : 0));
+    const int n_parked = my_long > 0 ? kGkWarps / 4 - my_long - g.long_share : 0;
+    const int bar_threads = 32 * (my_long + (n_parked > 0 ? n_parked : 0));
     if (long_warp && n_long) {
         for (;;) {
             unsigned w = 0;
@@ -790,7 +859,7 @@ __global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
             grid_item(g, w, lane, stash_warp, tbuf_warp);
         }
         if (n_parked > 0) asm volatile("bar.arrive 1, %0;" ::"r"(bar_threads) : "memory");
-    } else if (sub0 && n_long && !long_warp && (int)(warp >> 2) >= g.long_per_sm + g.long_share) {
+    } else if (sub0 && my_long > 0 && !long_warp && (int)(warp >> 2) >= my_long + g.long_share) {
         asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
     }
     // short queue.  (Pulling and preparing the next item before solving the current one was measured:
