@@ -212,6 +212,36 @@ def test_config2_full_resolution_sample_bit_exact(engine, oracle_mod):
         assert_f32_bits_equal(getattr(win_full, name)[idx], win_o[name], f"full-solve winners {name}")
 
 
+def test_queue_plans_do_not_change_results(engine, oracle_mod, monkeypatch):
+    """grid_kernel's scheduling (how many long items share a sub-partition, which warps are parked; chosen per
+    launch by grid_items_scan) must not leak into the results: the full config-2 solve of a fleet whose plan is
+    L = 3 (seed 45) gives the same bits under every forced plan, and the sampled models match the oracle."""
+    from workload_variant_autoscaler_b200 import config2_grid
+    full = synth_fleet(100, 4, seed=45)
+    grid = config2_grid()
+    ref_cells, ref_win = engine.grid_solve(full, grid, want_cells=True)   # automatic plan
+    for forced in ("0", "1", "2", "4"):
+        monkeypatch.setenv("WVA_GRID_LONG", forced)
+        cells, win = engine.grid_solve(full, grid, want_cells=True)
+        for k in ("flags", "ttft", "itl", "rho", "throughput"):
+            assert np.array_equal(cells[k].view(np.uint8), ref_cells[k].view(np.uint8)), f"plan {forced}: cells.{k}"
+        for k, v in win.columns().items():
+            assert np.array_equal(v.view(np.uint8), ref_win.columns()[k].view(np.uint8)), f"plan {forced}: winners.{k}"
+    monkeypatch.delenv("WVA_GRID_LONG")
+    idx = np.array([3, 58])
+    sub = full.take_servers(idx)
+    cells_o, win_o = oracle_mod.grid_solve(sub, grid, want_cells=True)
+    n_per = full.n_acc * 256 * 64
+    for j, srv in enumerate(idx):
+        for k in ("ttft", "itl", "rho", "throughput"):
+            assert_f32_bits_equal(ref_cells[k][srv * n_per:(srv + 1) * n_per], cells_o[k][j * n_per:(j + 1) * n_per], f"cells.{k}")
+        assert np.array_equal(ref_cells["flags"][srv * n_per:(srv + 1) * n_per], cells_o["flags"][j * n_per:(j + 1) * n_per])
+    for name in ("feasible", "acc", "replicas", "batch"):
+        assert np.array_equal(np.asarray(getattr(ref_win, name))[idx].astype(np.int64), win_o[name].astype(np.int64)), name
+    for name in ("cost", "value", "itl", "ttft", "rho", "max_rate"):
+        assert_f32_bits_equal(getattr(ref_win, name)[idx], win_o[name], f"winners {name}")
+
+
 def test_empty_and_degenerate_fleets(engine, oracle_mod):
     f0 = synth_fleet(4, 2, seed=1).take_servers(np.array([], dtype=np.int64))   # no servers
     cand, win = engine.solve(f0)
