@@ -80,3 +80,21 @@ def test_shard_and_gather_roundtrip():
     assert np.array_equal(out.replicas, np.arange(f.n_servers) + 1)
     assert np.array_equal(out.cost, (np.arange(f.n_servers) * 0.5).astype(np.float32))
     assert out.feasible.all()
+
+
+def test_as_c_cache_follows_the_arrays():
+    """Fleet.as_c caches its ctypes struct: in-place edits are seen through the same pointers, a re-attached
+    array gets a fresh pointer, and callers receive a private copy they may edit."""
+    import ctypes as C
+    f = synth_fleet(4, 2, seed=9)
+    c1 = f.as_c()
+    p1 = C.cast(c1.srv_arrival_rpm, C.c_void_p).value
+    f.srv_arrival_rpm[:] = 7.0                                   # in place: same buffer
+    c2 = f.as_c()
+    assert C.cast(c2.srv_arrival_rpm, C.c_void_p).value == p1 and c2.srv_arrival_rpm[0] == 7.0
+    c2.srv_model = None                                          # editing the returned struct ...
+    assert bool(f.as_c().srv_model)                              # ... does not poison the cache
+    f.srv_arrival_rpm = np.full(4, 3.0, np.float32)              # re-attached: new buffer
+    c3 = f.as_c()
+    assert C.cast(c3.srv_arrival_rpm, C.c_void_p).value == f.srv_arrival_rpm.ctypes.data
+    assert c3.srv_arrival_rpm[0] == 3.0 and c3.n_servers == 4
