@@ -450,9 +450,23 @@ __global__ void __launch_bounds__(128) grid_rows(GridArgs g) {
     const double* tab = toff >= 0 ? g.tab + 4 * toff : nullptr;
     const bool staged = toff >= 0 && g.Bmax <= kRowsSmemEntries;
     if (staged) {
+        // all of a thread's loads first, then its stores: one L2 round trip instead of one per iteration
         const double2* src = (const double2*)tab;
         double2* dst = (double2*)rows_tab;
-        for (int i = threadIdx.x; i < 2 * g.Bmax; i += blockDim.x) dst[i] = src[i];
+        const int n16 = 2 * g.Bmax;
+        for (int i0 = threadIdx.x; i0 < n16; i0 += 8 * blockDim.x) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n16) v[u] = src[i];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n16) dst[i] = v[u];
+            }
+        }
     }
     __syncthreads();
     float l2s0 = 0.f, ls_end = 0.f;
