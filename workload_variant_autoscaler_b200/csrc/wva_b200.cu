@@ -178,10 +178,6 @@ struct wva_handle {
 
 namespace {
 
-__global__ void fill_int(int* p, size_t n, int v) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
 
 // control block on the device: a handful of ints
 enum { CTRL_COUNTER = 0, CTRL_FB_COUNT = 1, CTRL_FB_STATUS = 2, CTRL_INTS = 8 };
@@ -731,18 +727,16 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     }
     // the tables are rebuilt on every call (only the host-side work lists are cached):
     // they are part of the evaluation, not an input
+    // [tables x batch] constants, then the [server x replica] rate block grid_rows fills (always allocated)
+    CK(h->d_pb.ensure(sizeof(float4) * ((size_t)h->grid_n_tab * std::max(B, 1) + (size_t)S * std::max(R, 1) + 1)));
     if (h->grid_n_tab) {
-        CK(h->d_pb.ensure(sizeof(float4) * ((size_t)h->grid_n_tab * std::max(B, 1) + (size_t)S * std::max(R, 1) + 1)));
         float4* d_pb = (float4*)h->d_pb.p;
-        float4* d_rt = d_pb + (size_t)h->grid_n_tab * std::max(B, 1);
         build_pair_tables<<<h->grid_n_tab, 128, 0, h->stream>>>(h->df, (const int*)h->d_tab_pair.p,
                                                                 (const long long*)h->d_tab_off.p,
                                                                 (const int*)h->d_tab_len.p, h->grid_n_tab,
                                                                 (double*)h->d_tab.p, (float*)h->d_ls.p,
                                                                 (const int*)h->d_grid_lists.p, B, d_pb);
-        if (S * R > 0)
-            grid_rates<<<(S * R + 255) / 256, 256, 0, h->stream>>>(h->df, (const int*)h->d_grid_lists.p + 3 * B, R, d_rt);
-        h->launches += 2;
+        h->launches += 1;
         CK(cudaGetLastError());
     }
     GridArgs& g = plan->args;
@@ -759,7 +753,7 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     g.pair_tab_off = d_pair_off;
     g.pair_tab_idx = d_pair_idx;
     g.pb = (const float4*)h->d_pb.p;
-    g.rt = g.pb + (size_t)h->grid_n_tab * std::max(B, 1);
+    g.rt = (float4*)h->d_pb.p + (size_t)h->grid_n_tab * std::max(B, 1);
     const unsigned long long n_cells = (unsigned long long)S * A * B * R;
     if (n_cells > 0xfffffff0ull) return h->fail(WVA_ERR_UNSUPPORTED, "grid too large for one call (>= 2^32 cells)");
     g.n_cells = (long long)n_cells;
@@ -821,8 +815,6 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
     const size_t n_best = (size_t)hf.S * hf.A * g.R;
     if (plan.n_cells == 0) CK(cudaEventRecord(h->ev_k0, h->stream));
     if (plan.n_cells > 0) {
-        CK(cudaMemsetAsync(g.cells.flags, 0, plan.n_cells, h->stream));
-        fill_int<<<(unsigned)((n_best + 255) / 256), 256, 0, h->stream>>>(g.best_rank, n_best, INT_MAX);
         CK(cudaMemsetAsync(g.item_count, 0, sizeof(unsigned) * (2 * kClasses + 32), h->stream));
         {
             const int rows_threads = g.R >= 128 ? 128 : (g.R > 32 ? 64 : 32);
@@ -833,13 +825,12 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
         grid_sort_local<<<plan.n_blocks, kSortThreads, 0, h->stream>>>(g);
         // one warp per item; the item count lives on the device, so launch for the worst case
         const size_t max_items = (plan.n_cells + 31) / 32 + (size_t)plan.n_blocks;
-        grid_items_scan<<<1, 256, 0, h->stream>>>(g);
         grid_items_scatter<<<(unsigned)((max_items + 255) / 256), 256, 0, h->stream>>>(g);
         h->launches++;
         CK(cudaEventRecord(h->ev_k0, h->stream));  // wva_last_kernel_ms = the dominant kernel alone
         const size_t smem = (size_t)kGkWarps * (kGridStash * 32 + kGkTabWin * 4) * sizeof(double);
         grid_kernel<<<(unsigned)h->sm_count, kGkThreads, smem, h->stream>>>(g);
-        h->launches += 4;
+        h->launches += 2;
     }
     CK(cudaEventRecord(h->ev_k1, h->stream));
     if (plan.n_cells > 0) {

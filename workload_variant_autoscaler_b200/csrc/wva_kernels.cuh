@@ -282,14 +282,6 @@ __global__ void __launch_bounds__(128) build_pair_tables(DevFleet f, const int* 
     }
 }
 
-__global__ void grid_rates(DevFleet f, const int* __restrict__ replicas, int R, float4* __restrict__ rt) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= f.S * R) return;
-    const int s = k / R, ri = k % R;
-    const float rate = __fdiv_rn(total_rate_of(f, s), (float)replicas[ri]);
-    const float lambda = __fdiv_rn(rate, 1000.0f);
-    rt[k] = make_float4(rate, lambda, log2f(lambda), 0.0f);
-}
 
 // ---------------------------------------------------------------------------
 // K2: candidate grid.
@@ -329,7 +321,7 @@ struct GridArgs {
     const long long* pair_tab_off;  // [S*A] entry offset of the pair's table (-1: none)
     const int* pair_tab_idx;        // [S*A] table index (for the ls / pb columns)
     const float4* pb;               // [n_tab * B] per (table, batch): rmax, log2 sN, ls[N-1], log2 s0
-    const float4* rt;               // [S * R] per (server, replica): rate, lambda, log2 lambda
+    float4* rt;               // [S * R] per (server, replica): rate, lambda, log2 lambda
     double* row_acc;                // [S*A*R] shared-chain results per (server, accelerator, replica)
     double* row_sump;
     int* row_j;                     // last state of the shared chain (INT_MAX: no sharing)
@@ -478,7 +470,14 @@ __global__ void __launch_bounds__(128) grid_rows(GridArgs g) {
         const size_t row = (size_t)sa * g.R + ri;
         int j = INT_MAX;
         double acc = 0.0, sump = 0.0;
-        const float4 rt = g.rt[s * g.R + ri];
+        // per-replica rate, lambda and log2(lambda) of the server (rate = total / replicas, lambda = rate / 1000): every pair CTA
+        // derives its own copy, the CTA of accelerator 0 publishes it for the later kernels; the
+        // (pair, replica) slot of the batch-rank minimum is reset here too
+        const float rate = __fdiv_rn(total_rate_of(f, s), (float)g.replicas[ri]);
+        const float lambda = __fdiv_rn(rate, 1000.0f);
+        const float4 rt = make_float4(rate, lambda, log2f(lambda), 0.0f);
+        if (sa == s * f.A) g.rt[s * g.R + ri] = rt;
+        g.best_rank[row] = INT_MAX;
         if (toff >= 0 && rt.x > 0.0f) {
             // skip rows whose chain is (by the log-domain estimate) still far from negligible at the end of
             // the table: they cannot be shared and would only burn Bmax steps to find that out
@@ -521,6 +520,7 @@ __device__ __forceinline__ unsigned seg_inc(unsigned* counters, int key) {
 // histogrammed, scanned and scattered without leaving the CTA.  Each run of 32 sorted cells
 // becomes one warp work item tagged with its (longest) class; grid_sort_items then orders the
 // items globally, so the launch is longest-first while a pair's cells stay adjacent.
+__device__ __forceinline__ void grid_items_plan(const GridArgs& g);
 __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
     __shared__ uint8_t keys[kSortChunk];
     __shared__ uint8_t sorted_keys[kSortChunk];
@@ -600,8 +600,10 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
                 const long long cell = (long long)row * R + ri;
                 if (cell < base || cell >= base + n_here) return;
                 int key = 255;
+                bool done_here = false;
                 if (toff >= 0 && !(c.rt.x <= 0.0f) && !(c.rt.x > pb.x) && K >= 2) {  // Analyze: queueanalyzer.go:135-143
                     if (c.jl != INT_MAX && b >= c.jl + 2 && K < (1 << 23)) {
+                        done_here = true;
                         // the whole solve is shared with the row: only the N-dependent tail is per cell
                         ModelStats st;
                         stats_from_row(c.acc, c.sump, b, c.rt.y, st);
@@ -619,6 +621,9 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
                 }
                 keys[cell - base] = (uint8_t)key;
                 if (key != 255) seg_inc(hist, key);  // class 255 (finished here / not analysable) needs no slot
+                // every cell's flag byte is written exactly once per solve: here (0) unless the cell was finished
+                // above; grid_kernel / grid_fallback overwrite it for the cells they analyse
+                if (!done_here) g.cells.flags[cell] = 0;
             };
             if ((unsigned)lane < R) do_cell(lane, c0, 0);
             if ((unsigned)lane + 32 < R) do_cell(lane + 32, c1, 1);
@@ -665,6 +670,17 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
                                  ((unsigned long long)cls << 40);
         agg_inc(g.item_count + 1, cls);  // global items-per-class histogram (warp-aggregated)
     }
+    // the last CTA to get here turns the global histogram into class cursors and plans grid_kernel's queues
+    // (one launch less than a separate single-CTA kernel)
+    __shared__ bool last_cta;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_cta = atomicAdd(g.item_count + 2 * kClasses + 6, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last_cta) {
+        __threadfence();
+        grid_items_plan(g);
+    }
 }
 
 // Global order of the warp items by class (longest first): class cursors from the global
@@ -682,32 +698,40 @@ constexpr int kGkLong = -1;    // long-item warps per CTA: automatic     // long
 __device__ __forceinline__ float class_len(int c) { return exp2f((float)(254 - c) * (1.0f / 12.0f)); }
 __device__ __forceinline__ float item_us(int c) { return 0.0987f * class_len(c) + 7.0f; }
 __device__ __forceinline__ float long_us(int c) { return 0.0564f * class_len(c) + 4.0f; }
-__global__ void __launch_bounds__(256) grid_items_scan(GridArgs g) {
+// Runs in ONE CTA of at least kClasses threads (the last CTA of grid_sort_local to finish); threads beyond
+// kClasses only take part in the barriers.
+__device__ __forceinline__ void grid_items_plan(const GridArgs& g) {
     __shared__ unsigned cnt[kClasses + 1];  // exclusive prefix of the class counts (cnt[kClasses] = all items)
     __shared__ float wrk[kClasses + 1];     // exclusive prefix of the classes' work (warp-microseconds)
     __shared__ unsigned s_cnt[kClasses];
     __shared__ float s_wrk[kClasses];
     const int c = threadIdx.x;
-    const unsigned mine = g.item_count[1 + c];
-    const float us = item_us(c);
-    s_cnt[c] = mine;
-    s_wrk[c] = c < 255 ? (float)mine * us : 0.0f;
+    const bool on = c < kClasses;
+    const unsigned mine = on ? __ldcg(g.item_count + 1 + c) : 0u;  // other CTAs' atomics: read at L2
+    if (on) {
+        s_cnt[c] = mine;
+        s_wrk[c] = c < 255 ? (float)mine * item_us(c) : 0.0f;
+    }
     __syncthreads();
     for (int d = 1; d < kClasses; d <<= 1) {  // inclusive Hillis-Steele scans
-        const unsigned a = c >= d ? s_cnt[c - d] : 0u;
-        const float w = c >= d ? s_wrk[c - d] : 0.0f;
+        const unsigned a = (on && c >= d) ? s_cnt[c - d] : 0u;
+        const float w = (on && c >= d) ? s_wrk[c - d] : 0.0f;
         __syncthreads();
-        s_cnt[c] += a;
-        s_wrk[c] += w;
+        if (on) {
+            s_cnt[c] += a;
+            s_wrk[c] += w;
+        }
         __syncthreads();
     }
-    cnt[c + 1] = s_cnt[c];
-    wrk[c + 1] = s_wrk[c];
+    if (on) {
+        cnt[c + 1] = s_cnt[c];
+        wrk[c + 1] = s_wrk[c];
+        g.item_count[1 + kClasses + c] = s_cnt[c] - mine;  // class cursors for grid_items_scatter
+    }
     if (c == 0) {
         cnt[0] = 0;
         wrk[0] = 0.0f;
     }
-    g.item_count[1 + kClasses + c] = s_cnt[c] - mine;  // class cursors for grid_items_scatter
     __syncthreads();
     // grid_kernel's queues: the long queue is the head of the sorted list, the short queue the rest.
     // How many long items share a sub-partition (L) is chosen per launch from a two-term model of the
