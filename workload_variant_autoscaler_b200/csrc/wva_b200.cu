@@ -839,7 +839,7 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
         h->launches++;
     }
     if (hf.S > 0) {
-        grid_finalize<<<hf.S, 128, 0, h->stream>>>(g, winners);
+        grid_finalize<<<hf.S, 256, 0, h->stream>>>(g, winners);
         h->launches++;
     }
     CK(cudaGetLastError());

@@ -948,7 +948,7 @@ __global__ void grid_fallback(GridArgs g, double* scratch, size_t slot_doubles, 
 // K3: per-server argmin.  One CTA per server: one candidate per (accelerator, replica
 // level) = its smallest feasible batch size; warp-shuffle reduction, cross-warp reduction
 // staged through shared memory.
-__global__ void __launch_bounds__(128) grid_finalize(GridArgs g, AllocCols winners) {
+__global__ void __launch_bounds__(256) grid_finalize(GridArgs g, AllocCols winners) {
     const DevFleet& f = g.f;
     const int s = blockIdx.x;
     Cand best = cand_nil();
@@ -982,7 +982,7 @@ __global__ void __launch_bounds__(128) grid_finalize(GridArgs g, AllocCols winne
         }
     }
     best = cand_warp_min(best);
-    __shared__ Cand sm[4];
+    __shared__ Cand sm[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) sm[warp] = best;
     __syncthreads();
