@@ -214,7 +214,7 @@ def test_config2_full_resolution_sample_bit_exact(engine, oracle_mod):
 
 def test_queue_plans_do_not_change_results(engine, oracle_mod, monkeypatch):
     """grid_kernel's scheduling (how many long items share a sub-partition, which warps are parked; chosen per
-    launch by grid_items_scan) must not leak into the results: the full config-2 solve of a fleet whose plan is
+    launch by grid_items_plan) must not leak into the results: the full config-2 solve of a fleet whose plan is
     L = 3 (seed 45) gives the same bits under every forced plan, and the sampled models match the oracle."""
     from workload_variant_autoscaler_b200 import config2_grid
     full = synth_fleet(100, 4, seed=45)

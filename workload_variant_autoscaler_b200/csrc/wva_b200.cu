@@ -1643,7 +1643,7 @@ int wva_dbg_prof(long long* out, int reset) {
     return (int)cudaMemcpyFromSymbol(out, wva::wva_prof, sizeof(long long) * 16);
 }
 #endif
-int wva_dbg_read_plan(wva_handle* h, unsigned* out32) {  // grid_items_scan's queue plan: item_count[2*kClasses+1 ..+31]
+int wva_dbg_read_plan(wva_handle* h, unsigned* out32) {  // grid_items_plan's queue plan: item_count[2*kClasses+1 ..+31]
     if (!h || !h->d_sort.p || !h->dbg_plan) return -1;
     return (int)cudaMemcpy(out32, h->dbg_plan, sizeof(unsigned) * 31, cudaMemcpyDeviceToHost);
 }

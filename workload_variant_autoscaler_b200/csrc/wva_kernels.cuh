@@ -1,9 +1,8 @@
 // wva_kernels.cuh — sm_100a kernels of the WVA optimizer hot path.
 //
 //   build_pair_tables   servRate[n] (+ double-word reciprocal) per (server, accelerator)
-//   grid_kernel    K2   one Analyze per (server, acc, batch, replica) cell, persistent
-//                       warps pulling (server, batch, 32-cell chunk) items, fused
-//                       feasibility + cost + transition penalty + warp-shuffle argmin
+//   grid_* kernels K2   one Analyze per (server, acc, batch, replica) cell: row sharing, length-class
+//                       sort, persistent warps pulling 32-cell items, fused feasibility + batch-rank minimum
 //   grid_fallback       stored-vector re-run of the rare cells the streaming solve bails on
 //   grid_finalize  K3   per-server argmin over partials (warp shuffle -> smem -> record)
 //   sz_* kernels   K1   CreateAllocation per (server, acc) candidate as rounds of sorted solve batches
@@ -286,13 +285,17 @@ __global__ void __launch_bounds__(128) build_pair_tables(DevFleet f, const int* 
 // ---------------------------------------------------------------------------
 // K2: candidate grid.
 //
-//   grid_estimate   per cell: gates + Analyze's rate checks, a cheap log-domain estimate of
-//                   the chain length, an 8-bit length class; per-block class histograms
-//   grid_scan       exclusive scan of the histograms (counting sort, step 2)
-//   grid_scatter    cell ids ordered by descending estimated chain length
-//   grid_kernel     32 cells of (nearly) equal chain length per warp: streaming solve,
-//                   metrics, SLO feasibility, per-cell columns, atomicMin of the smallest
-//                   feasible batch rank per (server, accelerator, replica)
+//   grid_rows        per (pair, replica level): the chain every large-enough batch size shares
+//                    (solve_row); also the (server, replica) rate block and the batch-rank reset
+//   grid_sort_local  per chunk of 8192 cells: gates + Analyze's rate checks; cells that share their
+//                    row's chain are finished inline; the others get a log-domain length estimate,
+//                    an 8-bit class and a local counting sort -> warp items; the last CTA plans
+//                    grid_kernel's queues (grid_items_plan)
+//   grid_items_scatter  items ordered globally, longest class first
+//   grid_kernel      persistent CTA per SM; warps pull items (32 cells of nearly equal chain length)
+//                    from a long and a short queue: streaming solve, metrics, SLO feasibility,
+//                    per-cell columns, atomicMin of the smallest feasible batch rank per
+//                    (server, accelerator, replica)
 //   grid_fallback   stored-vector re-run of the rare cells the streaming solve bails on
 //   grid_finalize   per-server argmin (warp shuffle -> shared memory -> winner record)
 //
@@ -336,7 +339,7 @@ struct GridArgs {
     int* fb_count;           // cells that need the stored-vector fallback
     long long* fb_cells;
     int fb_cap;
-    int long_per_sm;         // grid_kernel: long items per sub-partition 0 (< 0: chosen per launch by grid_items_scan)
+    int long_per_sm;         // grid_kernel: long items per sub-partition 0 (< 0: chosen per launch by grid_items_plan)
     int n_ctas;              // CTAs of grid_kernel (= SMs)
     int long_share;          // ... and how many other warps of that sub-partition may pull short items meanwhile
     int long_cls;            // items of class <= long_cls are "long" ...
@@ -685,7 +688,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
 
 // Global order of the warp items by class (longest first): class cursors from the global
 // histogram, then a multi-CTA scatter with warp-aggregated atomics.
-// grid_kernel's CTA shape (the kernel is further down; grid_items_scan plans its queues)
+// grid_kernel's CTA shape (the kernel is further down; grid_items_plan plans its queues)
 constexpr int kGkWarps = 16;    // 4 per sub-partition; 128 registers per thread keep the two FP64 chains of pass 2 apart
 constexpr int kGkThreads = kGkWarps * 32;
 constexpr int kGkTabWin = 32;  // table entries staged per warp (solve_shared_t STAGED)
@@ -879,7 +882,7 @@ __global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
     const bool sub0 = (warp & 3) == 0;
     // the long items are spread over as few CTAs as possible (long_per_sm per CTA): the other CTAs keep all
     // four sub-partitions for the short queue
-    const int per = (int)g.item_count[kQLongN + 3];  // long items per sub-partition, chosen by grid_items_scan
+    const int per = (int)g.item_count[kQLongN + 3];  // long items per sub-partition, chosen by grid_items_plan
     const int long_ctas = per > 0 ? (int)((n_long + per - 1) / per) : 0;
     const int my_long = (int)blockIdx.x < long_ctas ? per : 0;
     const bool long_warp = sub0 && (int)(warp >> 2) < my_long;
