@@ -312,3 +312,29 @@ def test_ties_resolve_to_lowest_accelerator(engine, oracle_mod):
     _, win_g = engine.solve(f)
     assert_allocs_equal(win_g, win_o, "tie winners")
     assert (np.asarray(win_g.acc)[np.asarray(win_g.feasible) == 1] == 0).all()
+
+
+def test_reference_flow_from_kubernetes_objects(engine, oracle_mod):
+    """SURVEY.md 8f ranks 1 + 3 around the CUDA path: ConfigMaps + VariantAutoscalings (the reference's
+    optimizer_test.go fixture, with load on two variants) -> adapters -> fleet -> wva_solve -> AllocationSolution ->
+    optimized allocs; identical to the same flow through the oracle."""
+    from tests.test_adapters import ACC_CM, SC_CM, _va
+    from workload_variant_autoscaler_b200 import Fleet, adapters
+    sd = adapters.create_system_data(ACC_CM, SC_CM)
+    vas = [_va(1), _va(2, arrival="600.0", replicas=2), _va(3, arrival="4200.5", replicas=1)]
+    for va in vas[1:]:
+        va["status"]["currentAlloc"]["load"].update(avgInputTokens="128", avgOutputTokens="256")
+    for va in vas:
+        _, cls = adapters.find_model_slo(SC_CM, va["spec"]["modelID"])
+        for prof in va["spec"]["modelProfile"]["accelerators"]:
+            adapters.add_model_accelerator_profile_to_system_data(sd, va["spec"]["modelID"], prof)
+        adapters.add_server_info_to_system_data(sd, va, cls, environ={})
+    fleet = Fleet.from_spec(sd["spec"])
+    _, win_o = oracle_mod.solve(fleet)
+    _, win_g = engine.solve(fleet)
+    assert_allocs_equal(win_g, win_o, "winners")
+    sol_g, sol_o = adapters.generate_solution(fleet, win_g), adapters.generate_solution(fleet, win_o)
+    assert sol_g == sol_o and len(sol_g["spec"]) == 3
+    opts = [adapters.create_optimized_alloc(v["metadata"]["name"], "default", sol_g) for v in vas]
+    assert opts[0]["numReplicas"] == 1 and all(o["accelerator"] == "A100" for o in opts)
+    assert opts[2]["numReplicas"] >= opts[1]["numReplicas"] >= 1
