@@ -338,3 +338,22 @@ def test_reference_flow_from_kubernetes_objects(engine, oracle_mod):
     opts = [adapters.create_optimized_alloc(v["metadata"]["name"], "default", sol_g) for v in vas]
     assert opts[0]["numReplicas"] == 1 and all(o["accelerator"] == "A100" for o in opts)
     assert opts[2]["numReplicas"] >= opts[1]["numReplicas"] >= 1
+
+
+def test_grid_randomised_small_fleets(engine, oracle_mod):
+    """Twenty seeded random fleets and grids (unsorted and repeated batch sizes / replica levels, keep-accelerator,
+    zero-load and missing-profile servers, several queue ratios): cells and winners bit-exact against the oracle."""
+    rng = np.random.default_rng(20260921)
+    for case in range(20):
+        S, A = int(rng.integers(1, 10)), int(rng.integers(1, 6))
+        fleet = synth_fleet(S, A, seed=1000 + case, keep_accelerator=bool(case % 3 == 0), zero_load_frac=0.15,
+                            tps_frac=0.3, server_batch=bool(case % 2))
+        fleet.max_queue_to_batch_ratio = int(rng.choice([1, 4, 10, 17]))
+        if case % 4 == 1 and S > 1:
+            fleet.perf_present[int(rng.integers(0, fleet.n_models)), int(rng.integers(0, A))] = 0
+        if case % 5 == 2:
+            fleet.srv_min_replicas[:] = rng.integers(0, 4, S)
+        nb, nr = int(rng.integers(1, 9)), int(rng.integers(1, 40))
+        batch = rng.integers(1, 97, nb)          # unsorted, possibly repeated
+        replicas = rng.integers(1, 70, nr)
+        _grid_check(engine, oracle_mod, fleet, Grid(batch, replicas))
