@@ -357,3 +357,21 @@ def test_grid_randomised_small_fleets(engine, oracle_mod):
         batch = rng.integers(1, 97, nb)          # unsorted, possibly repeated
         replicas = rng.integers(1, 70, nr)
         _grid_check(engine, oracle_mod, fleet, Grid(batch, replicas))
+
+
+def test_size_randomised_fleets(engine, oracle_mod):
+    """Twelve seeded random fleets through wva_solve (Size's two bisections + CreateAllocation + SolveUnlimited):
+    candidates and winners bit-exact against the oracle, across batch-size ranges and queue ratios."""
+    rng = np.random.default_rng(7)
+    for case in range(12):
+        S, A = int(rng.integers(2, 30)), int(rng.integers(1, 5))
+        choices = [(1, 2, 3), (4, 8, 16, 32), (64, 128, 256), (5, 77, 300)][case % 4]
+        fleet = synth_fleet(S, A, seed=500 + case, keep_accelerator=bool(case % 2), zero_load_frac=0.1, tps_frac=0.25,
+                            server_batch=bool(case % 3), max_batch_choices=choices)
+        fleet.max_queue_to_batch_ratio = int(rng.choice([2, 10, 25]))
+        if case % 4 == 3:
+            fleet.perf_at_tokens[:] = 64
+        cand_o, win_o = oracle_mod.solve(fleet)
+        cand_g, win_g = engine.solve(fleet)
+        assert_allocs_equal(cand_g, cand_o, f"candidates, case {case}")
+        assert_allocs_equal(win_g, win_o, f"winners, case {case}")
