@@ -375,3 +375,12 @@ def test_size_randomised_fleets(engine, oracle_mod):
         cand_g, win_g = engine.solve(fleet)
         assert_allocs_equal(cand_g, cand_o, f"candidates, case {case}")
         assert_allocs_equal(win_g, win_o, f"winners, case {case}")
+
+
+def test_grid_wide_replica_axis_and_long_tables(engine, oracle_mod):
+    """R = 100 replica levels (the per-lane row cache of grid_sort_local covers the first 64, the rest take the
+    generic path) and a 1700-entry table (longer than grid_rows' shared-memory staging; 18,700-state chains)."""
+    fleet = synth_fleet(2, 2, seed=77)
+    fleet.srv_arrival_rpm[:] = np.float32([900.0, 2500.0])
+    _grid_check(engine, oracle_mod, fleet, Grid([3, 1700], np.arange(1, 101)))
+    _grid_check(engine, oracle_mod, fleet, Grid([64, 7, 64], np.arange(100, 0, -1)))
