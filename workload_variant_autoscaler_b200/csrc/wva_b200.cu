@@ -1616,6 +1616,19 @@ __global__ void div_selfcheck_kernel(unsigned long long seed, int iters, unsigne
         z.yl = __dmul_rn(__fma_rn(-b, rc.yh, 1.0), rc.yh);
         const double q2 = div_recip(a, z);
         if (__double_as_longlong(q2) != __double_as_longlong(want)) ++bad;
+        // the tail step with the pre-multiplied low word (step_recip): p in [2^-280, 2^600), float32 lambda in
+        // [2^-60, 2^60]
+        {
+            const unsigned long long r3 = next();
+            const long long ep = (long long)(r3 % 881) - 280;
+            const double pp = __longlong_as_double((long long)(((unsigned long long)(1023 + ep) << 52) | ma));
+            const long long el = (long long)((r3 >> 12) % 121) - 60;
+            const double lam = __longlong_as_double(
+                (long long)(((unsigned long long)(1023 + el) << 52) | ((r3 >> 20) & 0x000FFFFFE0000000ull)));
+            const double got = step_recip(pp, lam, __dmul_rn(lam, rc.yl), rc);
+            const double want3 = __ddiv_rn(__dmul_rn(pp, lam), b);
+            if (__double_as_longlong(got) != __double_as_longlong(want3)) ++bad;
+        }
     }
     if (bad) atomicAdd(mismatches, bad);
 }
