@@ -134,3 +134,28 @@ def test_reference_flow_without_load_scales_to_min_replicas(oracle_mod, scale_to
     with pytest.raises(adapters.AdapterError):
         adapters.create_optimized_alloc("missing", "default", solution)
     assert adapters.replica_metrics(0, 3)["desired_ratio"] == 3.0 and adapters.replica_metrics(2, 3)["desired_ratio"] == 1.5
+
+
+def test_generate_solution_like_reference_system_test(oracle_mod):
+    """pkg/core/system_test.go:1413-1519 (TestSystem_GenerateSolution): one A100, one model, one server under
+    load -> the solution holds the server with an accelerator, a positive replica count and its load."""
+    spec = {
+        "acceleratorData": {"accelerators": [{"name": "A100", "type": "GPU_A100", "multiplicity": 1, "cost": 1.0}]},
+        "modelData": {"models": [{"name": "test-model", "acc": "A100", "accCount": 1, "maxBatchSize": 16, "atTokens": 100,
+                                  "decodeParms": {"alpha": 10.0, "beta": 2.0}, "prefillParms": {"gamma": 5.0, "delta": 0.1}}]},
+        "serviceClassData": {"serviceClasses": [{"name": "default", "priority": 1, "modelTargets": [
+            {"model": "test-model", "slo-itl": 100, "slo-ttft": 1000, "slo-tps": 50}]}]},
+        "serverData": {"servers": [{"name": "test-server", "model": "test-model", "class": "default", "minNumReplicas": 1,
+                                    "maxBatchSize": 16, "currentAlloc": {"accelerator": "A100", "numReplicas": 2, "load": {
+                                        "arrivalRate": 30, "avgInTokens": 100, "avgOutTokens": 200}}}]},
+        "optimizerData": {"optimizer": {"unlimited": True}},
+        "capacityData": {"count": []},
+    }
+    fleet = Fleet.from_spec(spec)
+    _, win = oracle_mod.solve(fleet)
+    sol = adapters.generate_solution(fleet, win)["spec"]
+    assert "test-server" in sol
+    alloc = sol["test-server"]
+    assert alloc["accelerator"] == "A100" and alloc["numReplicas"] > 0 and alloc["maxBatch"] == 16
+    assert alloc["load"] == {"arrivalRate": 30.0, "avgInTokens": 100, "avgOutTokens": 200}
+    assert alloc["cost"] == float(np.float32(1.0) * np.float32(alloc["numReplicas"]))   # accCost * instances * replicas
