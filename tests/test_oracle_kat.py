@@ -201,3 +201,54 @@ def test_ttft_itl_monotone_in_rate(oracle_mod):
     itl = [qa.eval_itl(float(x))[1] for x in xs]
     assert all(b >= a - 1e-4 for a, b in zip(ttft, ttft[1:]))
     assert all(b >= a - 1e-4 for a, b in zip(itl, itl[1:]))
+
+
+# ---- pkg/analyzer/queueanalyzer_test.go behaviour tests, through the oracle ----------------------------
+_TEST_CONFIG = dict(max_batch=8, max_queue=16, alpha=1.0, beta=0.01, gamma=10.0, delta=0.001)   # queueanalyzer_test.go:11-24
+
+
+def _qa(oracle_mod, in_tokens, out_tokens):
+    c = _TEST_CONFIG
+    return oracle_mod.Analyzer(c["max_batch"], c["max_queue"], c["alpha"], c["beta"], c["gamma"], c["delta"], in_tokens, out_tokens)
+
+
+def test_new_queue_analyzer_request_sizes(oracle_mod):  # queueanalyzer_test.go:26-90
+    for in_tok, out_tok in ((0, 10), (0, 1), (100, 1), (200, 20)):
+        assert _qa(oracle_mod, in_tok, out_tok) is not None
+    for in_tok, out_tok in ((0, 0), (-1, -1), (50, 0)):
+        with pytest.raises(ValueError):
+            _qa(oracle_mod, in_tok, out_tok)
+
+
+def test_build_model_rate_range(oracle_mod):  # queueanalyzer_test.go:317-355
+    qa = _qa(oracle_mod, 100, 10)
+    rmin, rmax = qa.rate_range()
+    assert 0 < rmin < rmax
+    assert qa.K == _TEST_CONFIG["max_batch"] + _TEST_CONFIG["max_queue"]
+    sr = qa.serv_rate()
+    assert sr.shape == (8,) and (np.diff(sr) > 0).all()          # more concurrency, more throughput (beta << alpha)
+
+
+def test_analyze_rate_cases(oracle_mod):  # queueanalyzer_test.go:357-446
+    qa = _qa(oracle_mod, 100, 10)
+    rmin, rmax = qa.rate_range()
+    f32 = np.float32
+    for rate in (0.0, -1.0, float(f32(rmax) * f32(1.1))):
+        err, m = qa.analyze(rate)
+        assert err != 0 and m is None
+    for rate in (float(f32(rmin) * f32(0.5)), float((f32(rmin) + f32(rmax)) * f32(0.5)), float(f32(rmax) * f32(0.9))):
+        err, m = qa.analyze(rate)
+        assert err == 0
+        for k in ("throughput", "avg_resp_time", "avg_wait_time", "avg_num_in_serv", "avg_prefill_time", "avg_token_time"):
+            assert m[k] >= 0, k
+        assert 0 <= m["rho"] <= 1
+
+
+def test_size_target_cases(oracle_mod):  # queueanalyzer_test.go:448-554
+    qa = _qa(oracle_mod, 100, 10)
+    for ttft, itl, tps in ((50.0, 5.0, 100.0), (0.0, 0.0, 0.0)):
+        err, rates, metrics, achieved = qa.size(ttft, itl, tps)
+        assert err == 0 and metrics is not None
+        assert all(v >= 0 for v in rates.values()) and all(v >= 0 for v in achieved.values())
+    for ttft, itl, tps in ((-1.0, 5.0, 100.0), (50.0, -1.0, 100.0), (50.0, 5.0, -1.0)):
+        assert qa.size(ttft, itl, tps)[0] != 0
