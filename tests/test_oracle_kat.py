@@ -252,3 +252,31 @@ def test_size_target_cases(oracle_mod):  # queueanalyzer_test.go:448-554
         assert all(v >= 0 for v in rates.values()) and all(v >= 0 for v in achieved.values())
     for ttft, itl, tps in ((-1.0, 5.0, 100.0), (50.0, -1.0, 100.0), (50.0, 5.0, -1.0)):
         assert qa.size(ttft, itl, tps)[0] != 0
+
+
+def test_eval_ttft_and_itl_cases(oracle_mod):  # pkg/analyzer/utils_test.go:383-519 (N = 4, queue 8)
+    qa = oracle_mod.Analyzer(4, 8, 1.0, 0.01, 10.0, 0.001, 100, 10)
+    for lam in (0.001, 0.01, 1.0):
+        err, ttft = qa.eval_ttft(lam)
+        assert err == 0 and ttft >= 10.0            # at least the base prefill time gamma
+        err, itl = qa.eval_itl(lam)
+        assert err == 0 and itl >= 1.0              # at least alpha
+
+
+def test_binary_search_with_analyzer_functions(oracle_mod):  # utils_test.go:521-608
+    qa = oracle_mod.Analyzer(4, 8, 1.0, 0.01, 10.0, 0.001, 100, 10)
+    rmin, rmax = qa.rate_range()
+    lmin, lmax = float(np.float32(rmin) / np.float32(1000)), float(np.float32(rmax) / np.float32(1000))
+
+    def ev(fn):
+        def f(x):
+            err, y = fn(x)
+            if err:
+                raise ValueError("invalid model")
+            return y
+        return f
+    for target, fn in ((25.0, qa.eval_ttft), (2.0, qa.eval_itl)):
+        err, xs, ind = oracle_mod.binary_search(lmin, lmax, target, ev(fn))
+        if err == 0 and ind == 0:                    # found inside the bracket: the target is met to 0.1
+            e2, y = fn(xs)
+            assert e2 == 0 and abs(y - target) <= 0.1
