@@ -92,6 +92,8 @@ def lib():
     L.wvao_mm1k_solve.argtypes = [vp, f, f, C.POINTER(ModelStats)]
     L.wvao_mm1k_probs.restype = C.POINTER(C.c_double)
     L.wvao_mm1k_probs.argtypes = [vp]
+    L.wvao_model_new_rates.restype = vp
+    L.wvao_model_new_rates.argtypes = [i, C.POINTER(C.c_float), i]
     L.wvao_analyzer_new.restype = vp
     L.wvao_analyzer_new.argtypes = [i, i, f, f, f, f, i, i]
     L.wvao_analyzer_free.argtypes = [vp]
@@ -200,6 +202,30 @@ class Analyzer:
     def eval_itl(self, x):
         y = C.c_float()
         return lib().wvao_eval_itl(self._h, x, C.byref(y)), y.value
+
+
+class StateDependentModel:
+    """analyzer.NewMM1ModelStateDependent(K, servRate) on its own (mm1modelstatedependent.go:16-24)."""
+
+    def __init__(self, K, serv_rate):
+        r = np.ascontiguousarray(serv_rate, np.float32)
+        self._h = lib().wvao_model_new_rates(int(K), r.ctypes.data_as(C.POINTER(C.c_float)), int(r.size))
+        if not self._h:
+            raise ValueError("invalid model")
+        self.K = int(K)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().wvao_analyzer_free(self._h)
+            self._h = None
+
+    def solve(self, lam, mu=1.0):
+        st = ModelStats()
+        lib().wvao_model_solve(self._h, lam, mu, C.byref(st))
+        return _st(st)
+
+    def probs(self):
+        return np.ctypeslib.as_array(lib().wvao_analyzer_probs(self._h), (self.K + 1,)).copy()
 
 
 class MM1K:

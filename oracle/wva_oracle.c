@@ -357,6 +357,23 @@ wvao_analyzer *wvao_analyzer_new(int max_batch, int max_queue, float alpha, floa
     return qa;
 }
 
+/* NewMM1ModelStateDependent(K, servRate) (mm1modelstatedependent.go:16-24) on its own: the reference's
+ * queuemodel_test.go builds models from arbitrary rate vectors, with K larger than the vector (the last rate
+ * then serves every deeper state, :80-84).  Only wvao_model_solve / probs / K are meaningful on the result. */
+wvao_analyzer *wvao_model_new_rates(int K, const float *serv_rate, int n) {
+    if (K < 0 || n <= 0 || !serv_rate) return NULL;
+    wvao_analyzer *qa = (wvao_analyzer *)calloc(1, sizeof(*qa));
+    if (!qa) return NULL;
+    qa->max_batch = n;
+    qa->max_queue = K - n;
+    qa->out_tokens = 1;
+    qa->serv_rate = (float *)malloc(sizeof(float) * (size_t)n);
+    for (int i = 0; i < n; i++) qa->serv_rate[i] = serv_rate[i];
+    qa->K = K;
+    qa->p = (double *)calloc((size_t)K + 1, sizeof(double));
+    return qa;
+}
+
 void wvao_analyzer_free(wvao_analyzer *qa) {
     if (!qa) return;
     free(qa->serv_rate);

@@ -84,6 +84,7 @@ const double *wvao_mm1k_probs(const wvao_mm1k *m);
 /* NewQueueAnalyzer / BuildModel: queueanalyzer.go:87-131. NULL on check() failure. */
 wvao_analyzer *wvao_analyzer_new(int max_batch, int max_queue, float alpha, float beta, float gamma,
                                  float delta, int in_tokens, int out_tokens);
+wvao_analyzer *wvao_model_new_rates(int K, const float *serv_rate, int n); /* NewMM1ModelStateDependent :16-24 */
 void wvao_analyzer_free(wvao_analyzer *qa);
 void wvao_analyzer_rate_range(const wvao_analyzer *qa, float *rmin, float *rmax);
 const float *wvao_analyzer_serv_rate(const wvao_analyzer *qa); /* [max_batch] */

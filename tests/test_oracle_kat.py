@@ -280,3 +280,33 @@ def test_binary_search_with_analyzer_functions(oracle_mod):  # utils_test.go:521
         if err == 0 and ind == 0:                    # found inside the bracket: the target is met to 0.1
             e2, y = fn(xs)
             assert e2 == 0 and abs(y - target) <= 0.1
+
+
+# ---- pkg/analyzer/queuemodel_test.go: MM1ModelStateDependent built from raw rate vectors --------------
+def test_state_dependent_solve_cases(oracle_mod):  # queuemodel_test.go:325-400
+    m = oracle_mod.StateDependentModel(5, [1.0, 2.0, 3.0])
+    for lam, want_valid in ((0.5, True), (1.5, True), (2.8, True), (0.0, True), (-1.0, False)):
+        st = m.solve(lam, 1.0)
+        assert bool(st["is_valid"]) == want_valid, lam
+        if want_valid:
+            assert st["avg_num_in_servers"] >= 0 and 0 <= st["rho"] <= 1
+            if st["avg_resp_time"] > 0 and st["throughput"] > 0:      # Little's law to 1e-4
+                assert abs(np.float32(st["throughput"]) * np.float32(st["avg_resp_time"]) - st["avg_num_in_system"]) <= 1e-4
+    # hand check at lambda = 0.5: p = (1, 1/2, 1/8, 1/48, 1/288, 1/1728) / sum
+    m.solve(0.5, 1.0)
+    w = np.array([1, 1 / 2, 1 / 8, 1 / 48, 1 / 288, 1 / 1728])
+    assert np.allclose(m.probs(), w / w.sum(), rtol=1e-15)
+
+
+def test_state_dependent_utilisation_is_one_minus_p0(oracle_mod):  # queuemodel_test.go:402-422
+    m = oracle_mod.StateDependentModel(4, [2.0, 4.0, 6.0])
+    st = m.solve(1.0, 1.0)
+    assert st["is_valid"] and abs(st["rho"] - np.float32(1.0 - np.float32(m.probs()[0]))) <= 1e-6
+
+
+def test_state_dependent_service_rate_extension(oracle_mod):  # queuemodel_test.go:424-441: K beyond the rate vector
+    m = oracle_mod.StateDependentModel(5, [1.0, 2.0])
+    st = m.solve(0.5, 1.0)
+    assert st["is_valid"] and st["avg_num_in_system"] >= 0 and st["throughput"] >= 0
+    w = np.array([1, 1 / 2, 1 / 8, 1 / 32, 1 / 128, 1 / 512])          # states 2.. are served at the last rate
+    assert np.allclose(m.probs(), w / w.sum(), rtol=1e-15)
