@@ -310,3 +310,30 @@ def test_state_dependent_service_rate_extension(oracle_mod):  # queuemodel_test.
     assert st["is_valid"] and st["avg_num_in_system"] >= 0 and st["throughput"] >= 0
     w = np.array([1, 1 / 2, 1 / 8, 1 / 32, 1 / 128, 1 / 512])          # states 2.. are served at the last rate
     assert np.allclose(m.probs(), w / w.sum(), rtol=1e-15)
+
+
+def test_candidate_accelerators_keep_rule(oracle_mod):  # pkg/core/server_test.go:395-466 (server.go:70-82)
+    from workload_variant_autoscaler_b200 import Fleet
+
+    def candidates(keep, cur_acc):
+        spec = {
+            "acceleratorData": {"accelerators": [{"name": n, "type": n, "multiplicity": 1, "cost": c}
+                                                 for n, c in (("gpu-a", 100.0), ("gpu-b", 150.0), ("gpu-c", 80.0))]},
+            "modelData": {"models": [{"name": "test-model", "acc": n, "accCount": 1, "maxBatchSize": 8,
+                                      "decodeParms": {"alpha": 5.0, "beta": 2.0}, "prefillParms": {"gamma": 10.0, "delta": 1.5}}
+                                     for n in ("gpu-a", "gpu-b", "gpu-c")]},
+            "serviceClassData": {"serviceClasses": [{"name": "default", "priority": 1, "modelTargets": [
+                {"model": "test-model", "slo-itl": 100, "slo-ttft": 1000}]}]},
+            "serverData": {"servers": [{"name": "test-server", "model": "test-model", "class": "default",
+                                        "keepAccelerator": keep, "minNumReplicas": 1,
+                                        "currentAlloc": {"accelerator": cur_acc, "load": {}}}]},
+            "optimizerData": {"optimizer": {"unlimited": True}}, "capacityData": {"count": []},
+        }
+        fleet = Fleet.from_spec(spec)
+        cand = oracle_mod.calculate(fleet)[0]                       # zero load: one zero-load allocation per candidate
+        return [fleet.acc_names[a] for a in range(fleet.n_acc) if cand["feasible"][a]]
+
+    assert candidates(False, "") == ["gpu-a", "gpu-b", "gpu-c"]            # no keep-accelerator constraint
+    assert candidates(True, "") == ["gpu-a", "gpu-b", "gpu-c"]             # keep, but no current accelerator
+    assert candidates(True, "gpu-b") == ["gpu-b"]                           # keep the current accelerator
+    assert candidates(True, "nonexistent-gpu") == []                        # current accelerator not in the system
