@@ -159,3 +159,26 @@ def test_generate_solution_like_reference_system_test(oracle_mod):
     assert alloc["accelerator"] == "A100" and alloc["numReplicas"] > 0 and alloc["maxBatch"] == 16
     assert alloc["load"] == {"arrivalRate": 30.0, "avgInTokens": 100, "avgOutTokens": 200}
     assert alloc["cost"] == float(np.float32(1.0) * np.float32(alloc["numReplicas"]))   # accCost * instances * replicas
+
+
+def test_parse_float32_round_trips_random_float32s():
+    """Every finite float32 prints (shortest repr and 60 significant digits) to a literal that parses back to
+    itself; the literal one float64-ulp above a float32 midpoint goes to the upper neighbour."""
+    rng = np.random.default_rng(99)
+    bits = rng.integers(0, 2 ** 32, 4000, dtype=np.uint64).astype(np.uint32)
+    vals = bits.view(np.float32)
+    vals = vals[np.isfinite(vals)]
+    for v in vals[:3000]:
+        for lit in (repr(float(v)), "%.60g" % float(v), "%.9e" % float(v)):
+            got, err = go_parse_float32(lit)
+            assert err is None and got.view(np.uint32) == v.view(np.uint32), (lit, got, v)
+    for v in vals[:300]:
+        if v <= 0 or not np.isfinite(np.nextafter(v, np.float32(np.inf))):
+            continue
+        up = np.nextafter(v, np.float32(np.inf))
+        mid = (float(v) + float(up)) / 2.0                      # exact in float64
+        above = np.nextafter(mid, np.inf)                       # one float64 ulp above the midpoint
+        got, _ = go_parse_float32("%.60g" % above)
+        assert got == up, (v, up, got)
+        got, _ = go_parse_float32("%.60g" % np.nextafter(mid, -np.inf))
+        assert got == v
