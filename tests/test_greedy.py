@@ -83,3 +83,57 @@ def test_greedy_matches_oracle(engine, oracle_mod, policy, delayed, cap):
     cand_g, win_g = engine.solve(f)
     assert_allocs_equal(win_g, win_o, f"greedy winners policy={policy} delayed={delayed} cap={cap}")
     assert_allocs_equal(cand_g, cand_o, "greedy candidates (after best-effort scaling)")
+
+
+# ---- the reference's own fixture (pkg/solver/greedy_test.go:13-208, setupTestSystemForGreedy) -----------
+def _ref_spec(servers, cap_a100=4, cap_h100=2, policy="None", delayed=False, hp_7b=(400, 20, 15)):
+    perf = lambda name, acc, cnt, mb, at, a, b, g, d: {  # noqa: E731
+        "name": name, "acc": acc, "accCount": cnt, "maxBatchSize": mb, "atTokens": at,
+        "decodeParms": {"alpha": a, "beta": b}, "prefillParms": {"gamma": g, "delta": d}}
+    tgt = lambda m, itl, ttft, tps: {"model": m, "slo-itl": itl, "slo-ttft": ttft, "slo-tps": tps}  # noqa: E731
+    return {
+        "acceleratorData": {"accelerators": [{"name": "A100", "type": "GPU_A100", "multiplicity": 1, "cost": 1.0},
+                                             {"name": "H100", "type": "GPU_H100", "multiplicity": 1, "cost": 2.0}]},
+        "modelData": {"models": [perf("llama-7b", "A100", 1, 16, 100, 10.0, 2.0, 5.0, 0.1),
+                                 perf("llama-7b", "H100", 1, 32, 100, 8.0, 1.5, 3.0, 0.08),
+                                 perf("llama-13b", "A100", 2, 8, 150, 15.0, 3.0, 8.0, 0.15),
+                                 perf("llama-13b", "H100", 1, 16, 150, 12.0, 2.5, 6.0, 0.12)]},
+        "serviceClassData": {"serviceClasses": [
+            {"name": "high-priority", "priority": 1, "modelTargets": [tgt("llama-7b", *hp_7b), tgt("llama-13b", 500, 25, 12)]},
+            {"name": "medium-priority", "priority": 2, "modelTargets": [tgt("llama-7b", 450, 22, 13), tgt("llama-13b", 550, 28, 10)]},
+            {"name": "low-priority", "priority": 3, "modelTargets": [tgt("llama-7b", 500, 25, 10)]}]},
+        "serverData": {"servers": servers},
+        "optimizerData": {"optimizer": {"unlimited": False, "saturationPolicy": policy, "delayedBestEffort": delayed}},
+        "capacityData": {"count": [{"type": "GPU_A100", "count": cap_a100}, {"type": "GPU_H100", "count": cap_h100}]},
+    }
+
+
+def _srv(name, model, cls, rate, intok, outtok, maxb):
+    return {"name": name, "model": model, "class": cls, "minNumReplicas": 1, "maxBatchSize": maxb,
+            "currentAlloc": {"load": {"arrivalRate": rate, "avgInTokens": intok, "avgOutTokens": outtok}}}
+
+
+def test_reference_basic_allocation(oracle_mod):
+    """greedy_test.go:252-306: server1 on llama-7b with lenient targets has candidate allocations and is served."""
+    from workload_variant_autoscaler_b200 import Fleet
+    servers = [_srv("server1", "llama-7b", "high-priority", 30, 100, 200, 16),
+               _srv("server2", "llama-13b", "medium-priority", 20, 150, 300, 256),
+               _srv("server3", "llama-7b", "low-priority", 10, 80, 150, 128)]
+    f = Fleet.from_spec(_ref_spec(servers, hp_7b=(100, 1000, 50)))
+    cand, win = oracle_mod.solve(f)
+    assert cand["feasible"][0].any(), "server1 should have candidate allocations"
+    assert win["feasible"][0] and win["replicas"][0] >= 1
+    assert (used_units(f, win) <= f.type_capacity).all()
+
+
+def test_reference_resource_exhaustion(oracle_mod):
+    """greedy_test.go:663-730: five llama-7b servers, one A100 and one H100, PriorityExhaustive + delayed best
+    effort: some server is served, not all of them are."""
+    from workload_variant_autoscaler_b200 import Fleet
+    servers = [_srv(f"server{i}", "llama-7b", "high-priority", 20, 100, 200, 16) for i in range(1, 6)]
+    f = Fleet.from_spec(_ref_spec(servers, cap_a100=1, cap_h100=1, policy="PriorityExhaustive", delayed=True,
+                                  hp_7b=(100, 1000, 50)))
+    _, win = oracle_mod.solve(f)
+    served = int(sum(1 for s in range(5) if win["feasible"][s] and win["replicas"][s] > 0))
+    assert 0 < served < 5
+    assert (used_units(f, win) <= f.type_capacity).all()
