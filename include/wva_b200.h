@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define WVA_ABI_VERSION 1
+#define WVA_ABI_VERSION 2
 
 /* ---- return codes ------------------------------------------------------- */
 #define WVA_OK 0
@@ -46,6 +46,7 @@ extern "C" {
 /* ---- sentinels ---------------------------------------------------------- */
 #define WVA_ACC_NONE (-1)    /* accelerator name "" (pkg/core/allocation.go:264)    */
 #define WVA_ACC_UNKNOWN (-2) /* a name that is not in the accelerator table         */
+#define WVA_ACC_ABSENT (-3)  /* no allocation at all: CreateAllocationDiff's "none"  */
 
 /* saturation policies: pkg/config/config.go:4-41 */
 #define WVA_SAT_NONE 0
@@ -229,6 +230,39 @@ int wva_grid_solve(wva_handle *h, const wva_fleet *fleet, const wva_grid *grid,
 
 /* Latency sweep of QueueAnalyzer.Analyze over n_rates rates per (server, acc). */
 int wva_sweep(wva_handle *h, const wva_fleet *fleet, int32_t n_rates, wva_sweep_out *out);
+
+/*
+ * What Manager.Optimize / Solver.Solve leave behind besides the per-server solution
+ * (pkg/manager/manager.go:21-27): the per-accelerator-type totals of System.AllocateByType
+ * (pkg/core/system.go:271-300) and the per-server orchestration differences of
+ * CreateAllocationDiff (pkg/core/allocation.go:353-380, collected by pkg/solver/solver.go:51-58).
+ * Any pointer may be NULL (that column is not written).
+ *
+ *   type_*  [T]: present = the type has an entry in the reference's allocationByType map (some
+ *                server was allocated an accelerator of that type); count = sum of
+ *                numReplicas * numInstances(model, acc) * multiplicity(acc); limit = capacity of the
+ *                type (0 when the capacity map has no entry); cost = sum of the allocations' cost.
+ *                The reference accumulates the float32 cost in Go map order (random); here the order
+ *                is ascending server index.
+ *   diff_*  [S]: old = CurrentAlloc of the server spec (always present: core/server.go:49), new = the
+ *                solution's allocation, accelerator WVA_ACC_ABSENT / 0 replicas / cost 0 when the
+ *                server got none ("none" in the reference); cost = newCost - oldCost.
+ */
+typedef struct wva_summary {
+    uint8_t *type_present;
+    int64_t *type_count;
+    int32_t *type_limit;
+    float *type_cost;
+    int32_t *diff_old_acc;
+    int32_t *diff_new_acc;
+    int32_t *diff_old_replicas;
+    int32_t *diff_new_replicas;
+    float *diff_cost;
+} wva_summary;
+
+/* Summary of the most recent wva_solve / wva_resolve / wva_grid_solve on this handle (the winners
+ * stay resident until the next call).  WVA_ERR_STATE when there is none. */
+int wva_summarize(wva_handle *h, wva_summary *out);
 
 /* ---- streaming reconcile (BASELINE config 5) ---------------------------- */
 

@@ -64,6 +64,10 @@ CELL_DTYPE = np.dtype([("flags", "u1"), ("ttft", "<f4"), ("itl", "<f4"), ("rho",
                       align=True)
 assert ALLOC_DTYPE.itemsize == C.sizeof(AllocRec) and CELL_DTYPE.itemsize == C.sizeof(CellRec)
 
+TYPE_TOTAL_DTYPE = np.dtype([("present", "<i4"), ("limit", "<i4"), ("count", "<i8"), ("cost", "<f4")], align=True)
+DIFF_DTYPE = np.dtype([("old_acc", "<i4"), ("new_acc", "<i4"), ("old_replicas", "<i4"), ("new_replicas", "<i4"),
+                       ("cost_diff", "<f4")])
+
 EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_float, C.POINTER(C.c_float))
 
 _lib = None
@@ -125,6 +129,8 @@ def lib():
     L.wvao_solve_unlimited.argtypes = [vp, vp, vp]
     L.wvao_solve_greedy.argtypes = [vp, vp, vp]
     L.wvao_solve.argtypes = [vp, vp, vp]
+    L.wvao_allocate_by_type.argtypes = [vp, vp, vp]
+    L.wvao_allocation_diffs.argtypes = [vp, vp, vp]
     L.wvao_grid_solve.argtypes = [vp, vp, vp, vp]
     L.wvao_grid_cells.argtypes = [vp, vp, C.c_int64, C.c_int64, vp]
     L.wvao_sweep.argtypes = [vp, i] + [vp] * 6
@@ -284,6 +290,25 @@ def solve(fleet, cand=None):
     fc = fleet.as_c()
     lib().wvao_solve(C.addressof(fc), cand.ctypes.data, win.ctypes.data)
     return cand, win
+
+
+def allocate_by_type(fleet, winners) -> np.ndarray:
+    """System.AllocateByType over a solution (structured winners [S]) -> structured array [T]."""
+    assert TYPE_TOTAL_DTYPE.itemsize == 24
+    out = np.zeros(fleet.n_types, TYPE_TOTAL_DTYPE)
+    win = np.ascontiguousarray(winners)
+    fc = fleet.as_c()
+    lib().wvao_allocate_by_type(C.addressof(fc), win.ctypes.data, out.ctypes.data)
+    return out
+
+
+def allocation_diffs(fleet, winners) -> np.ndarray:
+    """CreateAllocationDiff(current, solution) per server -> structured array [S]."""
+    out = np.zeros(fleet.n_servers, DIFF_DTYPE)
+    win = np.ascontiguousarray(winners)
+    fc = fleet.as_c()
+    lib().wvao_allocation_diffs(C.addressof(fc), win.ctypes.data, out.ctypes.data)
+    return out
 
 
 def grid_solve(fleet, grid, want_cells=True):

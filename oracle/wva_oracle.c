@@ -968,6 +968,53 @@ void wvao_solve(const wva_fleet *f, wvao_alloc *cand, wvao_alloc *winners) {
         wvao_solve_greedy(f, cand, winners);
 }
 
+/* System.AllocateByType: pkg/core/system.go:271-300.  The reference walks s.Servers() (a Go map, random
+ * order) and adds float32 costs as it goes; the order chosen here is ascending server index. */
+void wvao_allocate_by_type(const wva_fleet *f, const wvao_alloc *winners, wvao_type_total *out) {
+    for (int t = 0; t < f->n_types; ++t) {
+        out[t].present = 0;
+        out[t].limit = f->type_capacity[t]; /* s.capacity[nameType]: 0 when the map has no entry */
+        out[t].count = 0;
+        out[t].cost = 0.0f;
+    }
+    for (int s = 0; s < f->n_servers; ++s) {
+        const wvao_alloc *al = &winners[s];
+        if (!al->feasible) continue;                       /* serverAlloc == nil          :276-278 */
+        if (al->acc < 0 || al->acc >= f->n_acc) continue;  /* s.accelerators[""] == nil   :282-284 */
+        const int m = f->srv_model[s];
+        if (m < 0 || m >= f->n_models) continue;           /* model == nil                :282-284 */
+        const int t = f->acc_type[al->acc];
+        if (t < 0 || t >= f->n_types) continue;
+        out[t].present = 1;
+        /* model.numInstances[accName] is a map lookup: 0 when the model has no profile on acc */
+        const int64_t inst = f->perf_present[m * f->n_acc + al->acc] ? num_instances(f, m, al->acc) : 0;
+        out[t].count += (int64_t)al->replicas * inst * (int64_t)f->acc_multiplicity[al->acc]; /* :296 */
+        out[t].cost = out[t].cost + al->cost;                                                  /* :297 */
+    }
+}
+
+/* CreateAllocationDiff (pkg/core/allocation.go:353-380) as Solver.Solve applies it (solver.go:51-58):
+ * a = the server's current allocation (never nil: server.go:49), b = the solution's allocation. */
+void wvao_allocation_diffs(const wva_fleet *f, const wvao_alloc *winners, wvao_diff *out) {
+    for (int s = 0; s < f->n_servers; ++s) {
+        const wvao_alloc *b = &winners[s];
+        wvao_diff d;
+        d.old_acc = f->srv_cur_acc[s];
+        d.old_replicas = f->srv_cur_replicas[s];
+        const float old_cost = f->srv_cur_cost[s];
+        d.new_acc = WVA_ACC_ABSENT; /* "none" */
+        d.new_replicas = 0;
+        float new_cost = 0.0f;
+        if (b->feasible) {
+            d.new_acc = b->acc;
+            d.new_replicas = b->replicas;
+            new_cost = b->cost;
+        }
+        d.cost_diff = new_cost - old_cost;
+        out[s] = d;
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* candidate grid + latency sweep (the build's generalisation)  */
 /* ------------------------------------------------------------------------ */

@@ -132,6 +132,23 @@ void wvao_solve_greedy(const wva_fleet *f, wvao_alloc *cand, wvao_alloc *winners
 /* Solver.Solve: dispatch on f->unlimited. */
 void wvao_solve(const wva_fleet *f, wvao_alloc *cand, wvao_alloc *winners);
 
+/* ---- pkg/core/system.go:271-300, pkg/core/allocation.go:353-380 --------------------------- */
+typedef struct wvao_type_total { /* core.AllocationByType */
+    int32_t present;           /* the type has an entry in allocationByType */
+    int32_t limit;             /* s.capacity[type] */
+    int64_t count;
+    float cost;
+} wvao_type_total;
+/* System.AllocateByType over the solution `winners` [S] -> out [T]; float32 cost summed in ascending
+ * server index (the reference iterates a Go map, i.e. in random order). */
+void wvao_allocate_by_type(const wva_fleet *f, const wvao_alloc *winners, wvao_type_total *out);
+typedef struct wvao_diff { /* core.AllocationDiff */
+    int32_t old_acc, new_acc, old_replicas, new_replicas;
+    float cost_diff;
+} wvao_diff;
+/* CreateAllocationDiff(server.CurAllocation(), server.Allocation()) for every server (solver.go:51-58). */
+void wvao_allocation_diffs(const wva_fleet *f, const wvao_alloc *winners, wvao_diff *out);
+
 /* ---- grid / sweep (build's generalisation) --------------- */
 typedef struct wvao_cell {
     uint8_t flags; /* bit0 analyze ok, bit1 SLO feasible */

@@ -15,37 +15,10 @@ sys.path.insert(0, ROOT)
 
 import oracle  # noqa: E402
 from oracle import restate_np as R  # noqa: E402
-from workload_variant_autoscaler_b200 import Fleet, Grid, synth_fleet  # noqa: E402
+from workload_variant_autoscaler_b200 import Grid, synth_fleet  # noqa: E402
+from workload_variant_autoscaler_b200.fleet import CONFIG1_LOADS, CONFIG1_TOKENS, config1_fleet  # noqa: E402,F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-
-
-def config1_fleet(arrival_rpm, in_tok, out_tok):
-    """BASELINE configs[0]: the single VariantAutoscaling of deploy/examples/vllm-emulator
-    (vllme-variantautoscaling.yaml:26-37: A100 alpha 20.58 beta 0.41 gamma 5.2 delta 0.1, maxBatch 4;
-    deploy/configmap-*.yaml: A100 cost 40.00, Premium slo-tpot 24 / slo-ttft 500), production flags
-    (unlimited, keepAccelerator, minReplicas 1: internal/utils/utils.go:170-173,290)."""
-    spec = {
-        "acceleratorData": {"accelerators": [{"name": "A100", "type": "NVIDIA-A100-PCIE-80GB", "multiplicity": 1,
-                                              "cost": 40.0}]},
-        "modelData": {"models": [{"name": "default/default", "acc": "A100", "accCount": 1, "maxBatchSize": 4,
-                                  "decodeParms": {"alpha": 20.58, "beta": 0.41},
-                                  "prefillParms": {"gamma": 5.2, "delta": 0.1}}]},
-        "serviceClassData": {"serviceClasses": [{"name": "Premium", "priority": 1, "modelTargets": [
-            {"model": "default/default", "slo-itl": 24.0, "slo-ttft": 500.0}]}]},
-        "serverData": {"servers": [{"name": "vllme-deployment:llm-d-sim", "model": "default/default",
-                                    "class": "Premium", "keepAccelerator": True, "minNumReplicas": 1,
-                                    "maxBatchSize": 4,
-                                    "currentAlloc": {"accelerator": "A100", "numReplicas": 1, "cost": 40.0,
-                                                     "load": {"arrivalRate": arrival_rpm, "avgInTokens": in_tok,
-                                                              "avgOutTokens": out_tok}}}]},
-        "optimizerData": {"optimizer": {"unlimited": True}},
-    }
-    return Fleet.from_spec(spec)
-
-
-CONFIG1_LOADS = (0.0, 60.0, 480.0, 960.0, 1440.0)
-CONFIG1_TOKENS = ((0, 278), (128, 128))  # emulator through the collector; and the 128/128 variant
 
 
 def main():

@@ -32,7 +32,7 @@ def test_header_functions_are_exported(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.wva_abi_version() == 1
+    assert lib.wva_abi_version() == 2
     assert lib.wva_strerror(0) == b"ok"
     for code in (-1, -2, -3, -4, -5, -6, -99):
         assert len(lib.wva_strerror(code)) > 0
@@ -57,14 +57,15 @@ def test_struct_layouts_match_header_sizes():
     # wva_fleet: 4 sizes + 27 pointers + flags + tunables, padded as the C compiler pads it
     import subprocess
     import tempfile
-    prog = ('#include <stdio.h>\n#include "wva_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(wva_fleet), '
-            'sizeof(wva_allocs), sizeof(wva_grid));return 0;}')
+    prog = ('#include <stdio.h>\n#include "wva_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(wva_fleet), '
+            'sizeof(wva_allocs), sizeof(wva_grid), sizeof(wva_summary));return 0;}')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(prog)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"),
                         os.path.join(d, "t.c")], check=True)
         out = subprocess.run([os.path.join(d, "t")], check=True, capture_output=True, text=True).stdout.split()
-    assert [int(x) for x in out] == [C.sizeof(_abi.FleetC), C.sizeof(_abi.AllocsC), C.sizeof(_abi.GridC)]
+    assert [int(x) for x in out] == [C.sizeof(_abi.FleetC), C.sizeof(_abi.AllocsC), C.sizeof(_abi.GridC),
+                                     C.sizeof(_abi.SummaryC)]
 
 
 def test_create_without_gpu_fails_loudly(lib):

@@ -50,11 +50,38 @@ def test_parse_float32_is_go_strconv():
     v, err = go_parse_float32("1e39")
     assert np.isinf(v) and err == "range"
     assert go_parse_float32("3.4028235e38") == (np.finfo(np.float32).max, None)
-    for bad in ("", "abc", "1e", "0x1", "1_000", "+nan", "1.2.3", "e5"):
+    for bad in ("", "abc", "1e", "0x1", "+nan", "1.2.3", "e5", "1.5\n", " 1", "\u0661\u0662", "1_", "_1", "1__0", "1._5",
+                "1_.5"):
         assert go_parse_float32(bad) == (f32(0.0), "syntax"), bad
+    # Go's underscoreOK: underscores may separate digits (and follow a base prefix)
+    assert go_parse_float32("1_000") == (f32(1000.0), None)
+    assert go_parse_float32("0x_1p-2") == (f32(0.25), None) and go_parse_float32("1e1_0") == (f32(1e10), None)
     assert np.isinf(go_parse_float32("+Inf")[0]) and go_parse_float32("-infinity")[0] == f32("-inf")
     assert np.isnan(go_parse_float32("NaN")[0])
     assert np.signbit(go_parse_float32("-0")[0])
+
+
+def test_parse_float32_huge_exponents_are_decided_in_linear_time():
+    import time
+    f32 = np.float32
+    t0 = time.perf_counter()
+    v, err = go_parse_float32("1e999999999")
+    assert np.isposinf(v) and err == "range"
+    v, err = go_parse_float32("-1e999999999999999999999")
+    assert np.isneginf(v) and err == "range"
+    v, err = go_parse_float32("1e-9999999")
+    assert v == f32(0.0) and not np.signbit(v) and err is None
+    v, err = go_parse_float32("-0.0000001e-999999999")
+    assert v == f32(0.0) and np.signbit(v) and err is None
+    assert go_parse_float32("0x1p-200000") == (f32(0.0), None)
+    assert go_parse_float32("0x1p+99999999999")[1] == "range"
+    assert go_parse_float32("0e999999999") == (f32(0.0), None)            # zero mantissa: exponent is irrelevant
+    assert time.perf_counter() - t0 < 0.5
+    # the boundaries themselves still round exactly
+    assert go_parse_float32("1e-45")[0].view(np.uint32) == np.uint32(1) and go_parse_float32("1e-46")[0] == f32(0.0)
+    assert go_parse_float32("0x1p-149")[0].view(np.uint32) == np.uint32(1)
+    assert go_parse_float32("0x1.fffffep127") == (np.finfo(np.float32).max, None)
+    assert go_parse_float32("0x1p128")[1] == "range" and go_parse_float32("3.4028236e38")[1] == "range"
 
 
 def test_create_system_data_matches_reference_fixture():

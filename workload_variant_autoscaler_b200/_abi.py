@@ -19,6 +19,7 @@ WVA_ERR_UNSUPPORTED = -6
 
 ACC_NONE = -1      # accelerator name "" (pkg/core/allocation.go:264)
 ACC_UNKNOWN = -2   # a name missing from the accelerator table
+ACC_ABSENT = -3    # no allocation at all: CreateAllocationDiff's "none" (pkg/core/allocation.go:357-358)
 
 SAT_NONE, SAT_PRIORITY_EXHAUSTIVE, SAT_PRIORITY_ROUND_ROBIN, SAT_ROUND_ROBIN = 0, 1, 2, 3
 SAT_BY_NAME = {  # pkg/config/config.go:28-41
@@ -30,6 +31,7 @@ SAT_BY_NAME = {  # pkg/config/config.go:28-41
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
 u8p = C.POINTER(C.c_uint8)
 
 
@@ -104,11 +106,18 @@ class SweepOutC(C.Structure):
     _fields_ = [("valid", u8p), ("rate", f32p), ("ttft", f32p), ("itl", f32p), ("throughput", f32p), ("rho", f32p)]
 
 
-_CT = {np.dtype(np.float32): C.c_float, np.dtype(np.int32): C.c_int32, np.dtype(np.uint8): C.c_uint8}
+class SummaryC(C.Structure):
+    _fields_ = [("type_present", u8p), ("type_count", i64p), ("type_limit", i32p), ("type_cost", f32p),
+                ("diff_old_acc", i32p), ("diff_new_acc", i32p), ("diff_old_replicas", i32p),
+                ("diff_new_replicas", i32p), ("diff_cost", f32p)]
+
+
+_CT = {np.dtype(np.float32): C.c_float, np.dtype(np.int32): C.c_int32, np.dtype(np.uint8): C.c_uint8,
+       np.dtype(np.int64): C.c_int64}
 
 
 def ptr(a: np.ndarray):
-    """ctypes pointer to a C-contiguous numpy array of f32 / i32 / u8."""
+    """ctypes pointer to a C-contiguous numpy array of f32 / i32 / i64 / u8."""
     assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
     return a.ctypes.data_as(C.POINTER(_CT[a.dtype]))
 

@@ -36,31 +36,84 @@ class AdapterError(ValueError):
 # ----------------------------------------------------------------------------
 # strconv.ParseFloat(s, 32)
 # ----------------------------------------------------------------------------
-_DEC = re.compile(r"^([+-]?)(?:(\d+)(?:\.(\d*))?|\.(\d+))(?:[eE]([+-]?\d+))?$")
-_HEX = re.compile(r"^([+-]?)0[xX](?:([0-9a-fA-F]+)(?:\.([0-9a-fA-F]*))?|\.([0-9a-fA-F]+))[pP]([+-]?\d+)$")
+_DEC = re.compile(r"([+-]?)(?:([0-9]+)(?:\.([0-9]*))?|\.([0-9]+))(?:[eE]([+-]?[0-9]+))?")
+_HEX = re.compile(r"([+-]?)0[xX](?:([0-9a-fA-F]+)(?:\.([0-9a-fA-F]*))?|\.([0-9a-fA-F]+))[pP]([+-]?[0-9]+)")
 _F32_MAX = Fraction(int(np.finfo(np.float32).max))
 _F32_HALF_ULP_AT_MAX = Fraction(2) ** 103  # ulp(max) = 2^104
+_BIG, _TINY = object(), object()  # magnitude far outside float32: decided from the exponent alone, in O(len)
+
+
+def _underscore_ok(s: str) -> bool:
+    """strconv's underscoreOK: '_' only between digits, or between a base prefix and a digit."""
+    saw = "^"
+    i = 1 if s[:1] in "+-" else 0
+    hexa = False
+    if len(s) - i >= 2 and s[i] == "0" and s[i + 1] in "bBoOxX":
+        hexa = s[i + 1] in "xX"
+        i += 2
+        saw = "0"
+    for c in s[i:]:
+        if c in "0123456789" or (hexa and c in "abcdefABCDEF"):
+            saw = "0"
+        elif c == "_":
+            if saw != "0":
+                return False
+            saw = "_"
+        else:
+            if saw == "_":
+                return False
+            saw = "!"
+    return saw != "_"
+
+
+def _clamp_exp(ex: str) -> int:
+    """Exponent digits -> int without building huge integers (Go stops accumulating at 10000)."""
+    neg = ex[:1] == "-"
+    d = ex.lstrip("+-").lstrip("0")
+    v = 10 ** 6 if len(d) > 6 else int(d or "0")
+    return -v if neg else v
 
 
 def _exact_value(s: str):
-    """Exact rational value of a Go float literal, or None if the syntax is not accepted."""
-    m = _DEC.match(s)
+    """Exact rational value of a Go float literal; None if the syntax is not accepted; _BIG / _TINY (with the
+    sign as second element of a tuple) when the exponent alone puts it out of float32's range."""
+    if "_" in s:
+        if not _underscore_ok(s):
+            return None
+        s = s.replace("_", "")
+    m = _DEC.fullmatch(s)
     if m:
         sign, ip, fp, fp_only, ex = m.groups()
-        digits = (ip or "") + (fp or "") + (fp_only or "")
+        frac = (fp or "") + (fp_only or "")
+        digits = (ip or "") + frac
         if digits == "":
             return None
-        scale = len(fp or "") + len(fp_only or "")
-        v = Fraction(int(digits), 10 ** scale) * Fraction(10) ** int(ex or 0)
+        e = _clamp_exp(ex or "0")
+        sig = digits.lstrip("0")
+        if sig:
+            top = len(sig) - len(frac) + e  # value < 10^top, >= 10^(top-1)
+            if top > 45:
+                return (_BIG, sign)
+            if top < -60:
+                return (_TINY, sign)
+        v = Fraction(int(digits), 10 ** len(frac)) * Fraction(10) ** e
         return -v if sign == "-" else v
-    m = _HEX.match(s)
+    m = _HEX.fullmatch(s)
     if m:
         sign, ip, fp, fp_only, ex = m.groups()
-        digits = (ip or "") + (fp or "") + (fp_only or "")
+        frac = (fp or "") + (fp_only or "")
+        digits = (ip or "") + frac
         if digits == "":
             return None
-        scale = 4 * (len(fp or "") + len(fp_only or ""))
-        v = Fraction(int(digits, 16), 2 ** scale) * Fraction(2) ** int(ex)
+        e = _clamp_exp(ex)
+        sig = digits.lstrip("0")
+        if sig:
+            top = 4 * (len(sig) - len(frac)) + e  # value < 2^top, >= 2^(top-4)
+            if top > 140:
+                return (_BIG, sign)
+            if top < -200:
+                return (_TINY, sign)
+        v = Fraction(int(digits, 16), 2 ** (4 * len(frac))) * Fraction(2) ** e
         return -v if sign == "-" else v
     return None
 
@@ -80,9 +133,16 @@ def go_parse_float32(s: str):
         return np.float32("-inf" if low.startswith("-") else "inf"), None
     if body == "nan" and low == "nan":  # Go accepts "nan" without a sign only (plus case variants)
         return np.float32("nan"), None
+    if not s.isascii():
+        return np.float32(0.0), "syntax"
     x = _exact_value(s)
     if x is None:
         return np.float32(0.0), "syntax"
+    if isinstance(x, tuple):  # decided from the exponent: overflow is a range error, underflow rounds to +-0
+        kind, sign = x
+        if kind is _BIG:
+            return np.float32("-inf" if sign == "-" else "inf"), "range"
+        return np.float32(-0.0 if sign == "-" else 0.0), None
     if x == 0:
         return np.float32(-0.0 if s.startswith("-") else 0.0), None
     ax = abs(x)

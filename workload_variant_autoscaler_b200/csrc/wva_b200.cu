@@ -155,6 +155,12 @@ struct wva_handle {
         unsigned long long epoch = 0;
         int* d_err = nullptr;
     } xchg;
+    // the most recent solution (for wva_summarize): 0 none, 1 winner block on the device, 2 host copy (greedy)
+    int last_kind = 0;
+    std::vector<int32_t> last_acc, last_replicas;
+    std::vector<float> last_cost;
+    std::vector<uint8_t> last_feasible;
+    DevBuf d_summary;
     bool dbg_cycles = false;
     const unsigned* dbg_plan = nullptr;
     size_t dbg_n = 0;
@@ -394,6 +400,7 @@ int upload_fleet(wva_handle* h, const wva_fleet* f) {
     h->col_rate = c_rate; h->col_in = c_in; h->col_out = c_out;
     h->resident = true;
     h->epoch_tokens++;
+    h->last_kind = 0;
     return WVA_OK;
 }
 
@@ -1112,6 +1119,14 @@ int run_greedy_host(wva_handle* h, wva_allocs* candidates, wva_allocs* winners) 
     GreedySolver(hf, cand, win).run();
     cands_to_abi(cand, candidates);
     cands_to_abi(win, winners);
+    h->last_feasible.resize(hf.S); h->last_acc.resize(hf.S); h->last_replicas.resize(hf.S); h->last_cost.resize(hf.S);
+    for (int s = 0; s < hf.S; ++s) {
+        h->last_feasible[s] = win[s].feasible;
+        h->last_acc[s] = win[s].acc;
+        h->last_replicas[s] = win[s].replicas;
+        h->last_cost[s] = win[s].cost;
+    }
+    h->last_kind = 2;
     return WVA_OK;
 }
 
@@ -1175,7 +1190,7 @@ void wva_destroy(wva_handle* h) {
     DevBuf* bufs[] = {&h->arena, &h->d_cand_pair, &h->d_cand_N, &h->d_sz_tab, &h->d_sz_ls, &h->d_sz_off, &h->d_sz_state, &h->d_sz_req, &h->d_sz_sort, &h->d_grid_lists,
                       &h->d_pair_tab, &h->d_tab_pair, &h->d_tab_off, &h->d_tab_len, &h->d_tab, &h->d_ls, &h->d_sort, &h->d_best, &h->d_pb, &h->d_rows,
                       &h->d_cand_block, &h->d_win_block, &h->d_ctrl, &h->d_fb_list, &h->d_scratch,
-                      &h->d_cells, &h->d_sweep};
+                      &h->d_cells, &h->d_sweep, &h->d_summary, &h->d_dbg};
     for (DevBuf* b : bufs) b->release();
     h->stage.release();
     h->out_stage.release();
@@ -1358,6 +1373,7 @@ int wva_update_load(wva_handle* h, const float* arrival_rpm, const int32_t* in_t
     const size_t lo = h->col_rate.off, hi = h->col_out.off + h->col_out.bytes;
     if (S) CK(cudaMemcpyAsync((char*)h->arena.p + lo, (char*)h->stage.p + lo, hi - lo, cudaMemcpyHostToDevice, h->stream));
     if (tokens_changed || class_changed) h->epoch_tokens++;
+    h->last_kind = 0;
     return WVA_OK;
 }
 
@@ -1377,7 +1393,9 @@ int wva_resolve(wva_handle* h, wva_allocs* candidates, wva_allocs* winners) {
     CK(cudaSetDevice(h->device));
     if (!h->resident) return h->fail(WVA_ERR_STATE, "no resident fleet (call wva_upload first)");
     if (!h->hf.unlimited) return run_greedy_host(h, candidates, winners);
-    return run_size_host(h, candidates, winners);
+    const int rc = run_size_host(h, candidates, winners);
+    if (rc == WVA_OK) h->last_kind = 1;
+    return rc;
 }
 
 int wva_solve(wva_handle* h, const wva_fleet* fleet, wva_allocs* candidates, wva_allocs* winners) {
@@ -1474,6 +1492,91 @@ int wva_grid_solve(wva_handle* h, const wva_fleet* fleet, const wva_grid* grid, 
     rc = check_fallback_status(h, ctrl_host, plan.args.fb_cap);
     if (rc) return rc;
     scatter_block(hs, bw, winners);
+    h->last_kind = 1;
+    return WVA_OK;
+}
+
+// System.AllocateByType + CreateAllocationDiff over the most recent solution (include/wva_b200.h).
+int wva_summarize(wva_handle* h, wva_summary* out) {
+    if (!h || !out) return WVA_ERR_BAD_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!h->resident || h->last_kind == 0) return h->fail(WVA_ERR_STATE, "no solution to summarise (solve first)");
+    const HostFleet& hf = h->hf;
+    const size_t S = hf.S, T = hf.T;
+    if (h->last_kind == 2) {  // greedy winners live on the host: same loops as the kernel
+        for (size_t t = 0; t < T; ++t) {
+            if (out->type_present) out->type_present[t] = 0;
+            if (out->type_count) out->type_count[t] = 0;
+            if (out->type_limit) out->type_limit[t] = hf.type_capacity[t];
+            if (out->type_cost) out->type_cost[t] = 0.0f;
+        }
+        std::vector<float> cost(T, 0.0f);
+        std::vector<int64_t> cnt(T, 0);
+        for (size_t s = 0; s < S; ++s) {
+            const int feas = h->last_feasible[s], acc = h->last_acc[s], rep = h->last_replicas[s];
+            const float c = h->last_cost[s];
+            const int m = hf.srv_model[s];
+            if (feas && acc >= 0 && acc < hf.A && m >= 0 && m < hf.M) {
+                const int t = hf.acc_type[acc];
+                if (t >= 0 && t < hf.T) {
+                    int inst = 0;
+                    if (hf.perf_present[(size_t)m * hf.A + acc]) {
+                        inst = hf.perf_acc_count[(size_t)m * hf.A + acc];
+                        if (inst <= 0) inst = 1;
+                    }
+                    cnt[t] += (int64_t)rep * inst * (int64_t)hf.acc_mult[acc];
+                    cost[t] = cost[t] + c;
+                    if (out->type_present) out->type_present[t] = 1;
+                }
+            }
+            if (out->diff_old_acc) out->diff_old_acc[s] = hf.srv_cur_acc[s];
+            if (out->diff_old_replicas) out->diff_old_replicas[s] = hf.srv_cur_replicas[s];
+            if (out->diff_new_acc) out->diff_new_acc[s] = feas ? acc : WVA_ACC_ABSENT;
+            if (out->diff_new_replicas) out->diff_new_replicas[s] = feas ? rep : 0;
+            if (out->diff_cost) out->diff_cost[s] = (feas ? c : 0.0f) - hf.srv_cur_cost[s];
+        }
+        for (size_t t = 0; t < T; ++t) {
+            if (out->type_count) out->type_count[t] = cnt[t];
+            if (out->type_cost) out->type_cost[t] = cost[t];
+        }
+        return WVA_OK;
+    }
+    if (T > (size_t)kSumMaxTypes) return h->fail(WVA_ERR_UNSUPPORTED, "more accelerator types than summary_kernel owns");
+    // device winner block of the last solve
+    const Block bw = block_layout(S);
+    const AllocCols dw = block_cols(h->d_win_block.p, bw);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + std::max<size_t>(bytes, 1), 16); return at; };
+    const size_t o_cnt = take(8 * T), o_pres = take(T), o_lim = take(4 * T), o_cost = take(4 * T);
+    const size_t o_oa = take(4 * S), o_na = take(4 * S), o_or = take(4 * S), o_nr = take(4 * S), o_dc = take(4 * S);
+    CK(h->d_summary.ensure(o));
+    CK(h->out_stage.ensure(o));
+    char* d = (char*)h->d_summary.p;
+    SummaryOut so;
+    so.type_count = (long long*)(d + o_cnt);
+    so.type_present = (uint8_t*)(d + o_pres);
+    so.type_limit = (int*)(d + o_lim);
+    so.type_cost = (float*)(d + o_cost);
+    so.diff_old_acc = (int*)(d + o_oa);
+    so.diff_new_acc = (int*)(d + o_na);
+    so.diff_old_replicas = (int*)(d + o_or);
+    so.diff_new_replicas = (int*)(d + o_nr);
+    so.diff_cost = (float*)(d + o_dc);
+    summary_kernel<<<1, 256, 0, h->stream>>>(h->df, dw, so);
+    h->launches++;
+    CK(cudaGetLastError());
+    char* hs = (char*)h->out_stage.p;
+    CK(cudaMemcpyAsync(hs, d, o, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (out->type_count) memcpy(out->type_count, hs + o_cnt, 8 * T);
+    if (out->type_present) memcpy(out->type_present, hs + o_pres, T);
+    if (out->type_limit) memcpy(out->type_limit, hs + o_lim, 4 * T);
+    if (out->type_cost) memcpy(out->type_cost, hs + o_cost, 4 * T);
+    if (out->diff_old_acc) memcpy(out->diff_old_acc, hs + o_oa, 4 * S);
+    if (out->diff_new_acc) memcpy(out->diff_new_acc, hs + o_na, 4 * S);
+    if (out->diff_old_replicas) memcpy(out->diff_old_replicas, hs + o_or, 4 * S);
+    if (out->diff_new_replicas) memcpy(out->diff_new_replicas, hs + o_nr, 4 * S);
+    if (out->diff_cost) memcpy(out->diff_cost, hs + o_dc, 4 * S);
     return WVA_OK;
 }
 

@@ -1524,6 +1524,88 @@ __global__ void unlimited_kernel(DevFleet f, AllocCols cand, AllocCols winners) 
 }
 
 // ---------------------------------------------------------------------------
+// What Manager.Optimize / Solver.Solve leave behind next to the solution: System.AllocateByType
+// (pkg/core/system.go:271-300) and CreateAllocationDiff per server (pkg/core/allocation.go:353-380,
+// pkg/solver/solver.go:51-58).  One CTA: the diffs are element-wise; the per-type totals add float32
+// costs in ascending server index (the reference's own order is Go map order), so thread t owns type t
+// and walks the servers in order, chunk by chunk through shared memory (coalesced loads, serial adds).
+// ---------------------------------------------------------------------------
+struct SummaryOut {
+    uint8_t* type_present;
+    long long* type_count;
+    int* type_limit;
+    float* type_cost;
+    int *diff_old_acc, *diff_new_acc, *diff_old_replicas, *diff_new_replicas;
+    float* diff_cost;
+};
+constexpr int kSumChunk = 1024;
+constexpr int kSumMaxTypes = 1024;  // 256 threads x 4 owned types
+__global__ void __launch_bounds__(256) summary_kernel(DevFleet f, AllocCols win, SummaryOut o) {
+    __shared__ int s_type[kSumChunk];
+    __shared__ long long s_units[kSumChunk];
+    __shared__ float s_cost[kSumChunk];
+    // one accumulator set per owned type (thread t owns types t, t + 256, ...: at most 4 in registers)
+    constexpr int kOwn = 4;
+    long long cnt[kOwn];
+    float cost[kOwn];
+    int present[kOwn];
+#pragma unroll
+    for (int k = 0; k < kOwn; ++k) { cnt[k] = 0; cost[k] = 0.0f; present[k] = 0; }
+    for (int base = 0; base < f.S; base += kSumChunk) {
+        const int n = min(kSumChunk, f.S - base);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int s = base + i;
+            const int feas = win.feasible[s], acc = win.acc[s], rep = win.replicas[s];
+            const float c = win.cost[s];
+            int type = -1;
+            long long units = 0;
+            const int m = f.srv_model[s];
+            if (feas && acc >= 0 && acc < f.A && m >= 0 && m < f.M) {  // system.go:276-284
+                const int t = f.acc_type[acc];
+                if (t >= 0 && t < f.T) {
+                    type = t;
+                    const long long inst = f.perf_present[m * f.A + acc] ? num_instances(f, m, acc) : 0;
+                    units = (long long)rep * inst * (long long)f.acc_mult[acc];  // :296
+                }
+            }
+            s_type[i] = type;
+            s_units[i] = units;
+            s_cost[i] = c;
+            // CreateAllocationDiff(current, solution)
+            if (o.diff_old_acc) o.diff_old_acc[s] = f.srv_cur_acc[s];
+            if (o.diff_old_replicas) o.diff_old_replicas[s] = f.srv_cur_replicas[s];
+            if (o.diff_new_acc) o.diff_new_acc[s] = feas ? acc : -3;
+            if (o.diff_new_replicas) o.diff_new_replicas[s] = feas ? rep : 0;
+            if (o.diff_cost) o.diff_cost[s] = __fsub_rn(feas ? c : 0.0f, f.srv_cur_cost[s]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kOwn; ++k) {
+            const int t = threadIdx.x + k * blockDim.x;
+            if (t < f.T) {
+                for (int i = 0; i < n; ++i)
+                    if (s_type[i] == t) {
+                        present[k] = 1;
+                        cnt[k] += s_units[i];
+                        cost[k] = __fadd_rn(cost[k], s_cost[i]);  // :297, float32
+                    }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < kOwn; ++k) {
+        const int t = threadIdx.x + k * blockDim.x;
+        if (t < f.T) {
+            if (o.type_present) o.type_present[t] = (uint8_t)present[k];
+            if (o.type_count) o.type_count[t] = cnt[k];
+            if (o.type_limit) o.type_limit[t] = f.type_capacity[t];
+            if (o.type_cost) o.type_cost[t] = cost[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Latency sweep: warp = 32 consecutive rates of one (server, acc) pair.
 // ---------------------------------------------------------------------------
 struct SweepArgs {

@@ -34,7 +34,7 @@ class Engine:
         if rc != 0:
             raise WvaError(rc, self._L.wva_strerror(rc).decode() + " (the CUDA path has no CPU fallback)")
         self._h = h
-        self._fleet = None
+        self._n_servers = self._n_acc = None  # shape of the fleet resident on the device
 
     def close(self):
         if getattr(self, "_h", None):
@@ -56,6 +56,7 @@ class Engine:
         """``Server.Calculate`` for every server -> candidates [S*A] (pkg/core/server.go:55-67)."""
         cand = Allocs(fleet.n_servers * fleet.n_acc)
         fc, cc = fleet.as_c(), cand.as_c()
+        self._resident(fleet)
         self._check(self._L.wva_analyze(self._h, C.byref(fc), C.byref(cc)))
         return cand
 
@@ -65,6 +66,7 @@ class Engine:
         win = Allocs(fleet.n_servers)
         fc, wc = fleet.as_c(), win.as_c()
         cc = cand.as_c() if cand is not None else None
+        self._resident(fleet)
         self._check(self._L.wva_solve(self._h, C.byref(fc), C.byref(cc) if cc is not None else None, C.byref(wc)))
         return cand, win
 
@@ -85,6 +87,7 @@ class Engine:
                 cells[k] = np.zeros(n, np.float32)
             cc = _abi.CellsC(*[_abi.ptr(cells[k]) for k in ("flags", "ttft", "itl", "rho", "throughput")])
         fc, gc, wc = fleet.as_c(), grid.as_c(), win.as_c()
+        self._resident(fleet)
         self._check(self._L.wva_grid_solve(self._h, C.byref(fc), C.byref(gc), C.byref(cc) if cc is not None else None,
                                            C.byref(wc)))
         return cells, win
@@ -96,31 +99,65 @@ class Engine:
             out[k] = np.zeros(n, np.float32)
         oc = _abi.SweepOutC(*[_abi.ptr(out[k]) for k in ("valid", "rate", "ttft", "itl", "throughput", "rho")])
         fc = fleet.as_c()
+        self._resident(fleet)
         self._check(self._L.wva_sweep(self._h, C.byref(fc), n_rates, C.byref(oc)))
         return out
 
     # -- streaming reconcile ------------------------------------------------
+    def _resident(self, fleet: Fleet):
+        """Every call that takes a fleet makes it the handle's resident fleet (the C side re-uploads it);
+        ``resolve`` / ``update_load`` size their buffers from these counts, not from an older upload."""
+        self._n_servers, self._n_acc = fleet.n_servers, fleet.n_acc
+
     def upload(self, fleet: Fleet):
         fc = fleet.as_c()
         self._check(self._L.wva_upload(self._h, C.byref(fc)))
-        self._fleet = fleet
+        self._resident(fleet)
 
     def update_load(self, arrival_rpm=None, in_tokens=None, out_tokens=None):
+        if self._n_servers is None:
+            raise WvaError(_abi.WVA_ERR_STATE, "no resident fleet (call upload or a solve first)")
         a = np.ascontiguousarray(arrival_rpm, np.float32) if arrival_rpm is not None else None
         i = np.ascontiguousarray(in_tokens, np.int32) if in_tokens is not None else None
         o = np.ascontiguousarray(out_tokens, np.int32) if out_tokens is not None else None
+        for name, col in (("arrival_rpm", a), ("in_tokens", i), ("out_tokens", o)):
+            if col is not None and col.shape != (self._n_servers,):  # the C side copies exactly S entries
+                raise ValueError(f"{name} must have {self._n_servers} entries (one per resident server), "
+                                 f"got shape {col.shape}")
         self._check(self._L.wva_update_load(self._h, _abi.ptr(a) if a is not None else None,
                                             _abi.ptr(i) if i is not None else None,
                                             _abi.ptr(o) if o is not None else None))
 
     def resolve(self, want_candidates: bool = False):
-        f = self._fleet
-        cand = Allocs(f.n_servers * f.n_acc) if want_candidates else None
-        win = Allocs(f.n_servers)
+        if self._n_servers is None:
+            raise WvaError(_abi.WVA_ERR_STATE, "no resident fleet (call upload or a solve first)")
+        cand = Allocs(self._n_servers * self._n_acc) if want_candidates else None
+        win = Allocs(self._n_servers)
         wc = win.as_c()
         cc = cand.as_c() if cand is not None else None
         self._check(self._L.wva_resolve(self._h, C.byref(cc) if cc is not None else None, C.byref(wc)))
         return cand, win
+
+    def summarize(self, n_types: int) -> dict:
+        """``System.AllocateByType`` (pkg/core/system.go:271-300) and ``CreateAllocationDiff`` per server
+        (pkg/core/allocation.go:353-380) over the most recent solution of this engine.
+
+        Returns ``{"by_type": {present,count,limit,cost} arrays [T], "diff": {old_acc,new_acc,old_replicas,
+        new_replicas,cost} arrays [S]}``; accelerator ids use ``ACC_NONE`` for "" and ``ACC_ABSENT`` for
+        "none"."""
+        if self._n_servers is None:
+            raise WvaError(_abi.WVA_ERR_STATE, "no resident fleet (solve first)")
+        T, S = int(n_types), self._n_servers
+        by_type = {"present": np.zeros(T, np.uint8), "count": np.zeros(T, np.int64), "limit": np.zeros(T, np.int32),
+                   "cost": np.zeros(T, np.float32)}
+        diff = {"old_acc": np.zeros(S, np.int32), "new_acc": np.zeros(S, np.int32),
+                "old_replicas": np.zeros(S, np.int32), "new_replicas": np.zeros(S, np.int32),
+                "cost": np.zeros(S, np.float32)}
+        sc = _abi.SummaryC(_abi.ptr(by_type["present"]), _abi.ptr(by_type["count"]), _abi.ptr(by_type["limit"]),
+                           _abi.ptr(by_type["cost"]), _abi.ptr(diff["old_acc"]), _abi.ptr(diff["new_acc"]),
+                           _abi.ptr(diff["old_replicas"]), _abi.ptr(diff["new_replicas"]), _abi.ptr(diff["cost"]))
+        self._check(self._L.wva_summarize(self._h, C.byref(sc)))
+        return {"by_type": by_type, "diff": diff}
 
     # -- device-resident variants (multi-GPU driver, bench) -------------------
     def grid_solve_device(self, grid: Grid, winners_dev: _abi.AllocsC):

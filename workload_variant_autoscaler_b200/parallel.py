@@ -44,6 +44,10 @@ def solve_sharded(solve_local, fleet: Fleet, *, rank: int, world: int, all_gathe
     solve_local(shard: Fleet) -> Allocs of the shard's winners (the engine on this rank's GPU);
     all_gather(block: np.ndarray[int32]) -> np.ndarray [world, ...] (one collective).
     """
+    if not fleet.unlimited:
+        # the greedy pass shares ONE capacity map (pkg/solver/greedy.go:107-166): per-shard greedy solves would
+        # each spend the full capacity.  Limited mode shards the candidate generation only (solve_sharded_limited).
+        raise ValueError("solve_sharded needs an unlimited fleet; use solve_sharded_limited for greedy mode")
     shard = fleet.shard(rank, world)
     win = solve_local(shard)
     pad = (fleet.n_servers + world - 1) // world
