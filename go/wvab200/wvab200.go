@@ -5,9 +5,13 @@
 // ctypes harness in tests/.
 //
 // It replaces, behind the existing adapter types,
-//   - modelanalyzer.ModelAnalyzer.AnalyzeModel   (internal/modelanalyzer/analyzer.go:25-34)
-//   - optimizer.VariantAutoscalingsEngine.Optimize (internal/optimizer/optimizer.go:30-54)
-// i.e. Server.Calculate + Manager.Optimize + System.GenerateSolution of pkg/core, pkg/manager.
+//   - modelanalyzer.ModelAnalyzer.AnalyzeModel   (internal/modelanalyzer/analyzer.go:25-34)  -> ModelAnalyzer
+//   - optimizer.VariantAutoscalingsEngine.Optimize (internal/optimizer/optimizer.go:30-54)   -> VariantAutoscalingsEngine
+// i.e. Server.Calculate + Manager.Optimize + System.GenerateSolution of pkg/core, pkg/manager; plus
+//   - Engine.Upload / UpdateLoad / Resolve: the streaming reconcile (fleet resident on the GPU, only the load
+//     columns travel per tick: wva_upload / wva_update_load / wva_resolve)
+//   - Engine.Summarize: System.AllocateByType + Solver.Solve's allocation diffs (wva_summarize).
+// tests/c_abi/solve_smoke.c drives the same entry points from compiled C.
 package wvab200
 
 /*
@@ -34,12 +38,14 @@ import (
 const (
 	accNone    = -1 // accelerator name ""
 	accUnknown = -2 // a name that is not in the accelerator table
+	accAbsent  = -3 // no allocation at all ("none" in core.CreateAllocationDiff)
 )
 
 // Engine owns one wva_handle (one GPU). One solve at a time, like the reference L1.
 type Engine struct {
-	mu sync.Mutex
-	h  *C.wva_handle
+	mu   sync.Mutex
+	h    *C.wva_handle
+	last *fleet // the fleet of the most recent Solve / Upload (names for Summarize)
 }
 
 func NewEngine(device int) (*Engine, error) {
@@ -63,7 +69,7 @@ func (e *Engine) Close() {
 
 // fleet is the flat SoA image of config.SystemSpec (System.SetFromSpec's joins, done with maps here).
 type fleet struct {
-	accNames, serverNames                                      []string
+	accNames, serverNames, typeNames                           []string
 	accCost                                                    []float32
 	accMult, accType, typeCap                                  []int32
 	perfPresent                                                []uint8
@@ -75,23 +81,39 @@ type fleet struct {
 	curAcc, curRep                                             []int32
 	unlimited, delayedBestEffort                               bool
 	saturationPolicy                                           int
+	loads                                                      []config.ServerLoadSpec // per packed server
 }
 
 func pack(spec *config.SystemSpec) *fleet {
 	f := &fleet{}
 	accIdx, typeIdx, modelIdx := map[string]int{}, map[string]int{}, map[string]int{}
+	// AddAcceleratorFromSpec replaces an accelerator whose name repeats (pkg/core/system.go:99-101): the LAST
+	// spec wins, at the position of the first (same rule as Fleet.from_spec in the Python packer)
+	lastAcc := map[string]config.AcceleratorSpec{}
 	for _, a := range spec.Accelerators.Spec {
-		if _, dup := accIdx[a.Name]; dup {
-			continue
+		if _, dup := accIdx[a.Name]; !dup {
+			accIdx[a.Name] = len(f.accNames)
+			f.accNames = append(f.accNames, a.Name)
 		}
-		accIdx[a.Name] = len(f.accNames)
-		f.accNames = append(f.accNames, a.Name)
+		lastAcc[a.Name] = a
+	}
+	for _, name := range f.accNames {
+		a := lastAcc[name]
 		if _, ok := typeIdx[a.Type]; !ok {
 			typeIdx[a.Type] = len(typeIdx)
 		}
 		f.accCost = append(f.accCost, a.Cost)
 		f.accMult = append(f.accMult, int32(a.Multiplicity))
 		f.accType = append(f.accType, int32(typeIdx[a.Type]))
+	}
+	for _, c := range spec.Capacity.Count { // a capacity entry may name a type no accelerator has
+		if _, ok := typeIdx[c.Type]; !ok {
+			typeIdx[c.Type] = len(typeIdx)
+		}
+	}
+	f.typeNames = make([]string, len(typeIdx))
+	for name, t := range typeIdx {
+		f.typeNames[t] = name
 	}
 	f.typeCap = make([]int32, len(typeIdx))
 	for _, c := range spec.Capacity.Count {
@@ -136,8 +158,17 @@ func pack(spec *config.SystemSpec) *fleet {
 		}
 		classes[sc.Name] = c
 	}
+	// s.servers[v.Name] = ... (pkg/core/system.go:151-153): a repeated server name replaces the earlier spec
+	lastSrv := map[string]config.ServerSpec{}
 	for _, sv := range spec.Servers.Spec {
-		f.serverNames = append(f.serverNames, sv.Name)
+		if _, dup := lastSrv[sv.Name]; !dup {
+			f.serverNames = append(f.serverNames, sv.Name)
+		}
+		lastSrv[sv.Name] = sv
+	}
+	for _, name := range f.serverNames {
+		sv := lastSrv[name]
+		f.loads = append(f.loads, sv.CurrentAlloc.Load)
 		m, ok := modelIdx[sv.Model]
 		if !ok {
 			m = -1
@@ -205,13 +236,11 @@ func u8p(s []uint8) *C.uint8_t {
 	return (*C.uint8_t)(unsafe.Pointer(&s[0]))
 }
 
-// Solve = SetFromSpec + Server.Calculate for every server + Manager.Optimize + GenerateSolution.
-func (e *Engine) Solve(spec *config.SystemSpec) (*config.AllocationSolution, error) {
-	f := pack(spec)
-	S := len(f.serverNames)
-	var pin runtime.Pinner // the fleet struct holds Go pointers: pin them for the duration of the call
-	defer pin.Unpin()
+// cFleet fills the C image of a packed fleet.  The struct holds Go pointers: they are pinned on `pin` for the
+// duration of the call that uses it (cgo rule; the library never retains them, include/wva_b200.h).
+func cFleet(f *fleet, pin *runtime.Pinner) C.wva_fleet {
 	var cf C.wva_fleet
+	S := len(f.serverNames)
 	cf.n_acc, cf.n_types = C.int32_t(len(f.accNames)), C.int32_t(len(f.typeCap))
 	cf.n_models, cf.n_servers = C.int32_t(len(f.perfPresent)/max(len(f.accNames), 1)), C.int32_t(S)
 	cf.acc_cost, cf.acc_multiplicity, cf.acc_type, cf.type_capacity = f32p(f.accCost), i32p(f.accMult), i32p(f.accType), i32p(f.typeCap)
@@ -243,41 +272,287 @@ func (e *Engine) Solve(spec *config.SystemSpec) (*config.AllocationSolution, err
 	C.wva_tunables_default(&cf.tun)
 	cf.tun.max_queue_to_batch_ratio = C.int32_t(config.MaxQueueToBatchRatio)
 	cf.tun.accel_penalty_factor = C.float(config.AccelPenaltyFactor)
+	return cf
+}
 
-	feasible := make([]uint8, S)
-	acc, replicas, batch := make([]int32, S), make([]int32, S), make([]int32, S)
-	cost, itl, ttft := make([]float32, S), make([]float32, S), make([]float32, S)
-	var win C.wva_allocs
-	win.feasible, win.acc, win.replicas, win.batch = u8p(feasible), i32p(acc), i32p(replicas), i32p(batch)
-	win.cost, win.itl, win.ttft = f32p(cost), f32p(itl), f32p(ttft)
-	for _, p := range []unsafe.Pointer{unsafe.Pointer(win.feasible), unsafe.Pointer(win.acc), unsafe.Pointer(win.replicas),
-		unsafe.Pointer(win.batch), unsafe.Pointer(win.cost), unsafe.Pointer(win.itl), unsafe.Pointer(win.ttft)} {
+// allocs is the host SoA of core.Allocation records the library writes (wva_allocs).
+type allocs struct {
+	feasible                                []uint8
+	acc, replicas, batch                    []int32
+	cost, value, itl, ttft, rho, maxRate    []float32
+}
+
+func newAllocs(n int, pin *runtime.Pinner) (*allocs, C.wva_allocs) {
+	a := &allocs{feasible: make([]uint8, n), acc: make([]int32, n), replicas: make([]int32, n), batch: make([]int32, n),
+		cost: make([]float32, n), value: make([]float32, n), itl: make([]float32, n), ttft: make([]float32, n),
+		rho: make([]float32, n), maxRate: make([]float32, n)}
+	var c C.wva_allocs
+	c.feasible, c.acc, c.replicas, c.batch = u8p(a.feasible), i32p(a.acc), i32p(a.replicas), i32p(a.batch)
+	c.cost, c.value, c.itl, c.ttft, c.rho, c.max_rate = f32p(a.cost), f32p(a.value), f32p(a.itl), f32p(a.ttft), f32p(a.rho), f32p(a.maxRate)
+	for _, p := range []unsafe.Pointer{unsafe.Pointer(c.feasible), unsafe.Pointer(c.acc), unsafe.Pointer(c.replicas), unsafe.Pointer(c.batch),
+		unsafe.Pointer(c.cost), unsafe.Pointer(c.value), unsafe.Pointer(c.itl), unsafe.Pointer(c.ttft), unsafe.Pointer(c.rho),
+		unsafe.Pointer(c.max_rate)} {
+		if p != nil {
+			pin.Pin(p)
+		}
+	}
+	return a, c
+}
+
+func (e *Engine) fail(what string, rc C.int) error {
+	return fmt.Errorf("%s: %s: %s", what, C.GoString(C.wva_strerror(rc)), C.GoString(C.wva_last_error(e.h)))
+}
+
+// solution = System.GenerateSolution (pkg/core/system.go:303-319) over the winner records.
+func (f *fleet) solution(win *allocs) *config.AllocationSolution {
+	sol := &config.AllocationSolution{Spec: map[string]config.AllocationData{}}
+	for s := range f.serverNames {
+		if win.feasible[s] == 0 {
+			continue
+		}
+		name := ""
+		if win.acc[s] >= 0 {
+			name = f.accNames[win.acc[s]]
+		}
+		sol.Spec[f.serverNames[s]] = config.AllocationData{
+			Accelerator: name, NumReplicas: int(win.replicas[s]), MaxBatch: int(win.batch[s]), Cost: win.cost[s],
+			ITLAverage: win.itl[s], TTFTAverage: win.ttft[s], Load: f.loads[s],
+		}
+	}
+	return sol
+}
+
+// Solve = SetFromSpec + Server.Calculate for every server + Manager.Optimize + GenerateSolution.
+func (e *Engine) Solve(spec *config.SystemSpec) (*config.AllocationSolution, error) {
+	f := pack(spec)
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	cf := cFleet(f, &pin)
+	win, cwin := newAllocs(len(f.serverNames), &pin)
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if rc := C.wva_solve(e.h, &cf, nil, &cwin); rc != C.WVA_OK {
+		return nil, e.fail("wva_solve", rc)
+	}
+	e.last = f
+	return f.solution(win), nil
+}
+
+// CandidateAllocation is one entry of Server.AllAllocations() as the library computed it (core.Allocation's
+// fields are private to pkg/core; AllocationFromData covers the subset the CR status needs).
+type CandidateAllocation struct {
+	Data                  config.AllocationData // accelerator, numReplicas, maxBatch, cost, itl, ttft
+	Value, Rho            float32
+	MaxArrvRatePerReplica float32 // req/msec
+}
+
+// Analyze = Server.Calculate for every server (pkg/core/server.go:55-67): per server name, the candidate
+// allocation per accelerator name (nil candidates are absent, as in the reference's map).
+func (e *Engine) Analyze(spec *config.SystemSpec) (map[string]map[string]CandidateAllocation, error) {
+	f := pack(spec)
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	cf := cFleet(f, &pin)
+	A := len(f.accNames)
+	cand, ccand := newAllocs(len(f.serverNames)*A, &pin)
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if rc := C.wva_analyze(e.h, &cf, &ccand); rc != C.WVA_OK {
+		return nil, e.fail("wva_analyze", rc)
+	}
+	out := map[string]map[string]CandidateAllocation{}
+	for s, srv := range f.serverNames {
+		m := map[string]CandidateAllocation{}
+		for a := 0; a < A; a++ {
+			k := s*A + a
+			if cand.feasible[k] == 0 {
+				continue
+			}
+			name := ""
+			if cand.acc[k] >= 0 {
+				name = f.accNames[cand.acc[k]]
+			}
+			m[name] = CandidateAllocation{
+				Data: config.AllocationData{Accelerator: name, NumReplicas: int(cand.replicas[k]), MaxBatch: int(cand.batch[k]),
+					Cost: cand.cost[k], ITLAverage: cand.itl[k], TTFTAverage: cand.ttft[k], Load: f.loads[s]},
+				Value: cand.value[k], Rho: cand.rho[k], MaxArrvRatePerReplica: cand.maxRate[k],
+			}
+		}
+		out[srv] = m
+	}
+	return out, nil
+}
+
+// ---- streaming reconcile: the fleet stays resident on the GPU, only the load columns move per tick ----------
+
+// Resident is the handle-side image of the last Upload (names for reading results back).
+type Resident struct {
+	f *fleet
+}
+
+// Upload packs the spec once and makes it resident (wva_upload).
+func (e *Engine) Upload(spec *config.SystemSpec) (*Resident, error) {
+	f := pack(spec)
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	cf := cFleet(f, &pin)
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if rc := C.wva_upload(e.h, &cf); rc != C.WVA_OK {
+		return nil, e.fail("wva_upload", rc)
+	}
+	e.last = f
+	return &Resident{f: f}, nil
+}
+
+// UpdateLoad replaces the load of the named servers (collector output: internal/collector/collector.go:158-260)
+// and ships the three load columns (wva_update_load: 12 B per server).
+func (e *Engine) UpdateLoad(r *Resident, loads map[string]config.ServerLoadSpec) error {
+	f := r.f
+	for s, name := range f.serverNames {
+		if ld, ok := loads[name]; ok {
+			f.loads[s] = ld
+			f.arrival[s], f.inTok[s], f.outTok[s] = ld.ArrivalRate, int32(ld.AvgInTokens), int32(ld.AvgOutTokens)
+		}
+	}
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	pa, pi, po := f32p(f.arrival), i32p(f.inTok), i32p(f.outTok)
+	for _, p := range []unsafe.Pointer{unsafe.Pointer(pa), unsafe.Pointer(pi), unsafe.Pointer(po)} {
 		if p != nil {
 			pin.Pin(p)
 		}
 	}
 	e.mu.Lock()
-	rc := C.wva_solve(e.h, &cf, nil, &win)
-	msg := C.GoString(C.wva_last_error(e.h))
-	e.mu.Unlock()
-	if rc != C.WVA_OK {
-		return nil, fmt.Errorf("wva_solve: %s: %s", C.GoString(C.wva_strerror(rc)), msg)
+	defer e.mu.Unlock()
+	if rc := C.wva_update_load(e.h, pa, pi, po); rc != C.WVA_OK {
+		return e.fail("wva_update_load", rc)
 	}
-	sol := &config.AllocationSolution{Spec: map[string]config.AllocationData{}}
-	for s := 0; s < S; s++ { // GenerateSolution: pkg/core/system.go:303-319
-		if feasible[s] == 0 {
-			continue
-		}
-		name := ""
-		if acc[s] >= 0 {
-			name = f.accNames[acc[s]]
-		}
-		sol.Spec[f.serverNames[s]] = config.AllocationData{
-			Accelerator: name, NumReplicas: int(replicas[s]), MaxBatch: int(batch[s]), Cost: cost[s],
-			ITLAverage: itl[s], TTFTAverage: ttft[s], Load: spec.Servers.Spec[s].CurrentAlloc.Load,
+	return nil
+}
+
+// Resolve = Manager.Optimize + GenerateSolution on the resident fleet (wva_resolve).
+func (e *Engine) Resolve(r *Resident) (*config.AllocationSolution, error) {
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	win, cwin := newAllocs(len(r.f.serverNames), &pin)
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if rc := C.wva_resolve(e.h, nil, &cwin); rc != C.WVA_OK {
+		return nil, e.fail("wva_resolve", rc)
+	}
+	return r.f.solution(win), nil
+}
+
+// ---- System.AllocateByType + Solver.Solve's diffs ---------------------------------------------------------
+
+// TypeTotal mirrors core.AllocationByType (pkg/core/system.go:60-65).
+type TypeTotal struct {
+	Count, Limit int
+	Cost         float32
+}
+
+// Diff mirrors core.AllocationDiff (pkg/core/allocation.go:344-350); accelerator "none" = no allocation.
+type Diff struct {
+	OldAccelerator, NewAccelerator string
+	OldNumReplicas, NewNumReplicas int
+	CostDiff                       float32
+}
+
+// Summarize reads both for the most recent Solve / Resolve on this engine (wva_summarize).
+func (e *Engine) Summarize() (map[string]TypeTotal, map[string]Diff, error) {
+	f := e.last
+	if f == nil {
+		return nil, nil, fmt.Errorf("wva_summarize: no solution yet")
+	}
+	typeNames := f.typeNames
+	T, S := len(f.typeCap), len(f.serverNames)
+	present, count, limit, cost := make([]uint8, T), make([]int64, T), make([]int32, T), make([]float32, T)
+	oa, na, or, nr, dc := make([]int32, S), make([]int32, S), make([]int32, S), make([]int32, S), make([]float32, S)
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	var cs C.wva_summary
+	cs.type_present, cs.type_limit, cs.type_cost = u8p(present), i32p(limit), f32p(cost)
+	if T > 0 {
+		cs.type_count = (*C.int64_t)(unsafe.Pointer(&count[0]))
+	}
+	cs.diff_old_acc, cs.diff_new_acc, cs.diff_old_replicas, cs.diff_new_replicas, cs.diff_cost = i32p(oa), i32p(na), i32p(or), i32p(nr), f32p(dc)
+	for _, p := range []unsafe.Pointer{unsafe.Pointer(cs.type_present), unsafe.Pointer(cs.type_count), unsafe.Pointer(cs.type_limit),
+		unsafe.Pointer(cs.type_cost), unsafe.Pointer(cs.diff_old_acc), unsafe.Pointer(cs.diff_new_acc), unsafe.Pointer(cs.diff_old_replicas),
+		unsafe.Pointer(cs.diff_new_replicas), unsafe.Pointer(cs.diff_cost)} {
+		if p != nil {
+			pin.Pin(p)
 		}
 	}
-	return sol, nil
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if rc := C.wva_summarize(e.h, &cs); rc != C.WVA_OK {
+		return nil, nil, e.fail("wva_summarize", rc)
+	}
+	name := func(a int32) string {
+		switch {
+		case a >= 0:
+			return f.accNames[a]
+		case a == accAbsent:
+			return "none"
+		default:
+			return "" // accNone; an unknown current accelerator keeps the name it had in the spec
+		}
+	}
+	byType := map[string]TypeTotal{}
+	for t := 0; t < T; t++ {
+		if present[t] != 0 {
+			byType[typeNames[t]] = TypeTotal{Count: int(count[t]), Limit: int(limit[t]), Cost: cost[t]}
+		}
+	}
+	diffs := map[string]Diff{}
+	for s, srv := range f.serverNames {
+		diffs[srv] = Diff{OldAccelerator: name(oa[s]), NewAccelerator: name(na[s]), OldNumReplicas: int(or[s]),
+			NewNumReplicas: int(nr[s]), CostDiff: dc[s]}
+	}
+	return byType, diffs, nil
+}
+
+// ---- drop-ins for the controller's two adapter types -------------------------------------------------------
+
+// ModelAnalyzer is the drop-in for internal/modelanalyzer.ModelAnalyzer (analyzer.go:12-34): the controller
+// calls AnalyzeModel once per server in a loop (variantautoscaling_controller.go:148-156); the first call
+// analyses the WHOLE fleet in one device call and the rest read the cached table.
+type ModelAnalyzer struct {
+	engine *Engine
+	spec   *config.SystemSpec
+	once   sync.Once
+	table  map[string]map[string]CandidateAllocation
+	err    error
+}
+
+func NewModelAnalyzer(engine *Engine, spec *config.SystemSpec) *ModelAnalyzer {
+	return &ModelAnalyzer{engine: engine, spec: spec}
+}
+
+// ModelAcceleratorAllocation carries what interfaces.ModelAcceleratorAllocation carries (types.go:12-18); the
+// embedded *inferno.Allocation of the original is replaced by its exported data, because core.Allocation cannot
+// be built outside pkg/core with rho / maxArrvRatePerReplica set.
+type ModelAcceleratorAllocation struct {
+	Allocation         CandidateAllocation
+	RequiredPrefillQPS float64
+	RequiredDecodeQPS  float64
+	Reason             string
+}
+
+// AnalyzeModel mirrors analyzer.go:25-34 + CreateModelAnalyzeResponseFromAllocations (utils.go:9-24): an unknown
+// server yields an empty response, never an error.
+func (ma *ModelAnalyzer) AnalyzeModel(ctx context.Context, va llmdOptv1alpha1.VariantAutoscaling) (map[string]*ModelAcceleratorAllocation, error) {
+	ma.once.Do(func() { ma.table, ma.err = ma.engine.Analyze(ma.spec) })
+	if ma.err != nil {
+		return nil, ma.err
+	}
+	out := map[string]*ModelAcceleratorAllocation{}
+	for acc, c := range ma.table[utils.FullName(va.Name, va.Namespace)] {
+		qps := float64(c.MaxArrvRatePerReplica * 1000) // float32 product first, as alloc.MaxArrvRatePerReplica() * 1000
+		out[acc] = &ModelAcceleratorAllocation{Allocation: c, RequiredPrefillQPS: qps, RequiredDecodeQPS: qps, Reason: "markovian analysis"}
+	}
+	return out, nil
 }
 
 // VariantAutoscalingsEngine is the drop-in for internal/optimizer.VariantAutoscalingsEngine

@@ -655,7 +655,7 @@ struct GridPlan {
 
 // Per-cell columns kept on the device for every grid solve: flags + ttft/itl/rho (+ throughput
 // when the caller asked for the cell table).
-int ensure_cells(wva_handle* h, GridPlan& plan, bool want_throughput) {
+int ensure_cells(wva_handle* h, GridPlan& plan, bool want_cells, bool want_throughput) {
     const size_t nc = std::max<size_t>(plan.n_cells, 1);
     const size_t bytes = align_up(nc) + 4 * align_up(4 * nc);
     CK(h->d_cells.ensure(bytes));
@@ -665,6 +665,7 @@ int ensure_cells(wva_handle* h, GridPlan& plan, bool want_throughput) {
     plan.args.cells.itl = (float*)(p + align_up(nc) + align_up(4 * nc));
     plan.args.cells.rho = (float*)(p + align_up(nc) + 2 * align_up(4 * nc));
     plan.args.cells.throughput = want_throughput ? (float*)(p + align_up(nc) + 3 * align_up(4 * nc)) : nullptr;
+    plan.args.want_cells = want_cells ? 1 : 0;
     return WVA_OK;
 }
 
@@ -1434,7 +1435,7 @@ int wva_grid_solve_device(wva_handle* h, const wva_grid* grid, wva_allocs* winne
     GridPlan plan;
     rc = prepare_grid(h, grid, &plan);
     if (rc) return rc;
-    rc = ensure_cells(h, plan, false);
+    rc = ensure_cells(h, plan, false, false);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev_d0, h->stream));
     rc = enqueue_grid(h, plan, cols_from_abi(winners_dev));
@@ -1462,7 +1463,7 @@ int wva_grid_solve(wva_handle* h, const wva_fleet* fleet, const wva_grid* grid, 
     // per-cell columns live on the device for every solve; they travel to the host only on request
     const size_t nc = plan.n_cells;
     const bool want_cells = cells && (cells->flags || cells->ttft || cells->itl || cells->rho || cells->throughput);
-    rc = ensure_cells(h, plan, want_cells && cells->throughput);
+    rc = ensure_cells(h, plan, want_cells, want_cells && cells->throughput);
     if (rc) return rc;
     if (want_cells && nc)  // cells that are never analysed must read back as 0
         CK(cudaMemsetAsync(h->d_cells.p, 0, align_up(nc) + 4 * align_up(4 * nc), h->stream));

@@ -336,6 +336,8 @@ struct GridArgs {
     unsigned* item_count;    // [0] number of items, [1..256] items per class, [257..512] class cursors
     int* best_rank;          // [S*A*R] smallest feasible batch rank (INT_MAX: none)
     CellCols cells;          // internal per-cell columns (ttft, itl, rho always present)
+    int want_cells;          // 0: the caller did not ask for the cell table -> cells that share their row's chain store
+                             // nothing (grid_finalize recomputes the few winners among them); 1: every cell is stored
     int* fb_count;           // cells that need the stored-vector fallback
     long long* fb_cells;
     int fb_cap;
@@ -430,6 +432,50 @@ __device__ __forceinline__ void store_cell(const GridArgs& g, long long cell, in
     g.cells.itl[cell] = m.avg_token_time;
     g.cells.rho[cell] = m.rho;
     if (g.cells.throughput) g.cells.throughput[cell] = m.throughput;
+}
+
+// A cell that shares its row's chain (grid_sort_local): stats_from_row + metrics_from with everything that does
+// not depend on the batch size hoisted — per pair (PairConst: the operands of EffectiveConcurrency, PrefillTime,
+// DecodeTime), per (pair, replica level) (resp = avgNumInSystem / throughput, 1 - sumP).  Same operations in the
+// same order on the same operands as the unhoisted functions, hence the same bits.
+struct PairConst {
+    float gamma, d_in, alpha, beta, ec_base, ec_den;
+    int in_zero;
+};
+__device__ __forceinline__ PairConst pair_const(const QParams& q) {
+    PairConst pc;
+    const float tokens = (float)(q.out_tok - 1);                    // queueanalyzer.go:296-302
+    pc.gamma = q.gamma;
+    pc.alpha = q.alpha;
+    pc.beta = q.beta;
+    pc.d_in = __fmul_rn(q.delta, (float)q.in_tok);                  // delta * inTokens (:258, :300)
+    pc.ec_base = __fadd_rn(q.gamma, __fmul_rn(q.alpha, tokens));
+    pc.ec_den = __fadd_rn(pc.d_in, __fmul_rn(q.beta, tokens));
+    pc.in_zero = q.in_tok == 0;
+    return pc;
+}
+// resp: (float)acc / throughput with throughput = lambda * (1 - 0) = lambda
+__device__ __forceinline__ float row_resp_time(double acc, float lambda) {
+    return __fdiv_rn((float)acc, __fmul_rn(lambda, __fsub_rn(1.0f, 0.0f)));
+}
+__device__ __forceinline__ Metrics shared_cell_metrics(const PairConst& pc, double acc, double one_m_sump, float resp,
+                                                       float lambda, int N) {
+    const double in_serv = __dadd_rn(acc, __dmul_rn(one_m_sump, (double)N));  // mm1modelstatedependent.go:53
+    const float in_serv_f = (float)in_serv;
+    const float thr = __fmul_rn(lambda, __fsub_rn(1.0f, 0.0f));
+    const float serv = __fdiv_rn(in_serv_f, thr);
+    float w = __fsub_rn(resp, serv);
+    if (w < 0.0f) w = 0.0f;
+    const float fN = (float)N;
+    const float eff = go_minf(go_maxf(__fdiv_rn(__fsub_rn(serv, pc.ec_base), pc.ec_den), 0.0f), fN);
+    Metrics m;
+    m.avg_prefill_time = pc.in_zero ? 0.0f : __fadd_rn(pc.gamma, __fmul_rn(pc.d_in, eff));
+    m.avg_token_time = __fadd_rn(pc.alpha, __fmul_rn(pc.beta, eff));
+    m.rho = go_minf(go_maxf(__fdiv_rn(in_serv_f, fN), 0.0f), 1.0f);
+    m.throughput = __fmul_rn(thr, 1000.0f);
+    m.avg_wait_time = w;
+    m.ttft = __fadd_rn(w, m.avg_prefill_time);
+    return m;
 }
 
 // One CTA per (server, accelerator) pair, one lane per replica level: the chain every large-enough
@@ -555,7 +601,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
         // lane's own row constants (its first two replica levels: rate, lambda, the row's shared chain)
         struct LaneRow {
             float4 rt;
-            double acc, sump;
+            double acc, one_m_sump;  // shared-chain results of the row: sum(i p[i]), 1 - sumP
+            float resp;              // avgNumInSystem / throughput (does not depend on the batch size)
             int jl, rep;
         };
         LaneRow c0{}, c1{};
@@ -563,7 +610,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
         int bi = (int)(row0 + warp - sa * B);
         int s = 0, t = 0;
         long long toff = -1;
-        QParams q{};
+        PairConst pc{};
         FeasRow fr{};
         auto load_lane = [&](unsigned ri, LaneRow& c) {
             if (ri >= R || toff < 0) return;
@@ -571,7 +618,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
             c.rt = g.rt[(unsigned)s * R + ri];
             c.jl = g.row_j[rowid];
             c.acc = g.row_acc[rowid];
-            c.sump = g.row_sump[rowid];
+            c.one_m_sump = __dsub_rn(1.0, g.row_sump[rowid]);
+            c.resp = row_resp_time(c.acc, c.rt.y);
             c.rep = g.replicas[ri];
         };
         for (unsigned row = row0 + warp; row <= row1; row += kSortThreads / 32, bi += kSortThreads / 32) {
@@ -586,7 +634,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
                 toff = g.pair_tab_off[sa];
                 if (toff >= 0) {
                     t = g.pair_tab_idx[sa];
-                    q = qparams_of(f, s, (int)(sa - (unsigned)s * A));
+                    pc = pair_const(qparams_of(f, s, (int)(sa - (unsigned)s * A)));
                 }
                 fr = feas_row(f, s, 0.0f);
                 load_lane(lane, c0);
@@ -596,7 +644,7 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
             const int K = b + b * f.ratio;
             float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
             if (toff >= 0) pb = g.pb[(size_t)t * g.B + bi];
-            fr.lim = feas_lim(pb.x);
+            if (fr.tps) fr.lim = feas_lim(pb.x);
             const int rank = g.batch_rank[bi];
             // one cell: (row, ri) with the lane's cached row constants
             auto do_cell = [&](unsigned ri, const LaneRow& c, int slot) {
@@ -608,11 +656,9 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
                     if (c.jl != INT_MAX && b >= c.jl + 2 && K < (1 << 23)) {
                         done_here = true;
                         // the whole solve is shared with the row: only the N-dependent tail is per cell
-                        ModelStats st;
-                        stats_from_row(c.acc, c.sump, b, c.rt.y, st);
-                        const Metrics m = metrics_from(q, b, st);
+                        const Metrics m = shared_cell_metrics(pc, c.acc, c.one_m_sump, c.resp, c.rt.y, b);
                         const bool feas = cell_feasible(fr, c.rep, c.rt.y, m);
-                        store_cell(g, cell, 1, feas ? 1 : 0, m);
+                        if (g.want_cells) store_cell(g, cell, 1, feas ? 1 : 0, m);
                         if (feas) {
                             if (slot == 0) best0 = min(best0, rank);
                             else if (slot == 1) best1 = min(best1, rank);
@@ -624,9 +670,8 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
                 }
                 keys[cell - base] = (uint8_t)key;
                 if (key != 255) seg_inc(hist, key);  // class 255 (finished here / not analysable) needs no slot
-                // every cell's flag byte is written exactly once per solve: here (0) unless the cell was finished
-                // above; grid_kernel / grid_fallback overwrite it for the cells they analyse
-                if (!done_here) g.cells.flags[cell] = 0;
+                // (the cell table, when requested, is cleared by the host before the launch: cells that are never
+                // analysed read back as 0 without a store per cell here)
             };
             if ((unsigned)lane < R) do_cell(lane, c0, 0);
             if ((unsigned)lane + 32 < R) do_cell(lane + 32, c1, 1);
@@ -950,49 +995,127 @@ __global__ void grid_fallback(GridArgs g, double* scratch, size_t slot_doubles, 
 
 // K3: per-server argmin.  One CTA per server: one candidate per (accelerator, replica
 // level) = its smallest feasible batch size; warp-shuffle reduction, cross-warp reduction
-// staged through shared memory.
+// staged through shared memory.  The order (value, cost, replicas, batch, accelerator) does not involve the
+// latency metrics, so only the keys are reduced; the winner's itl / ttft / rho are fetched once at the end:
+// from the cell columns, or — for a cell that shares its row's chain and was not stored (want_cells == 0) —
+// by the same stats_from_row + metrics_from evaluation grid_sort_local ran for it.
+struct GridKey {
+    float value, cost;
+    int replicas, batch, acc, bi, ri, feasible;  // bi < 0: zero-load allocation of accelerator ri
+};
+__device__ __forceinline__ bool key_better(const GridKey& x, const GridKey& y) {
+    if (!x.feasible) return false;
+    if (!y.feasible) return true;
+    if (x.value != y.value) return x.value < y.value;
+    if (x.cost != y.cost) return x.cost < y.cost;
+    if (x.replicas != y.replicas) return x.replicas < y.replicas;
+    if (x.batch != y.batch) return x.batch < y.batch;
+    return x.acc < y.acc;
+}
+__device__ __forceinline__ GridKey key_warp_min(GridKey c) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        GridKey o;
+        o.value = __shfl_down_sync(0xffffffffu, c.value, d);
+        o.cost = __shfl_down_sync(0xffffffffu, c.cost, d);
+        o.replicas = __shfl_down_sync(0xffffffffu, c.replicas, d);
+        o.batch = __shfl_down_sync(0xffffffffu, c.batch, d);
+        o.acc = __shfl_down_sync(0xffffffffu, c.acc, d);
+        o.bi = __shfl_down_sync(0xffffffffu, c.bi, d);
+        o.ri = __shfl_down_sync(0xffffffffu, c.ri, d);
+        o.feasible = __shfl_down_sync(0xffffffffu, c.feasible, d);
+        if (key_better(o, c)) c = o;
+    }
+    return c;
+}
 __global__ void __launch_bounds__(256) grid_finalize(GridArgs g, AllocCols winners) {
     const DevFleet& f = g.f;
     const int s = blockIdx.x;
-    Cand best = cand_nil();
+    GridKey best{};
+    best.acc = -1;
     for (int k = threadIdx.x; k < f.A * g.R; k += blockDim.x) {
         const int a = k / g.R, ri = k % g.R;
         const int rank = g.best_rank[((size_t)s * f.A + a) * g.R + ri];
         if (rank == INT_MAX) continue;
         const int bi = g.rank_to_bi[rank];
         const int r = g.replicas[ri];
-        const long long cell = (((long long)s * f.A + a) * g.B + bi) * g.R + ri;
         Cand c = cand_nil();
         const long long total = (long long)num_instances(f, f.srv_model[s], a) * (long long)r;
-        c.feasible = 1;
         c.acc = a;
         c.replicas = r;
-        c.batch = g.batch[bi];
         c.cost = __fmul_rn(f.acc_cost[a], (float)total);
-        c.value = penalty_of(f, s, c);
-        c.itl = g.cells.itl[cell];
-        c.ttft = g.cells.ttft[cell];
-        c.rho = g.cells.rho[cell];
-        c.max_rate = __fdiv_rn(rate_max_of((float)g.tab[4 * (g.pair_tab_off[s * f.A + a] + c.batch - 1)]), 1000.0f);
-        if (cand_better(c, best)) best = c;
+        GridKey key;
+        key.value = penalty_of(f, s, c);
+        key.cost = c.cost;
+        key.replicas = r;
+        key.batch = g.batch[bi];
+        key.acc = a;
+        key.bi = bi;
+        key.ri = ri;
+        key.feasible = 1;
+        if (key_better(key, best)) best = key;
     }
     // zero-traffic servers: the reference's zeroLoadAllocation per candidate accelerator
     for (int a = threadIdx.x; a < f.A; a += blockDim.x) {
         if (pair_class(f, s, a, true) == PAIR_ZERO) {
             Cand c = zero_load_alloc(f, s, a);
-            c.value = penalty_of(f, s, c);
-            if (cand_better(c, best)) best = c;
+            GridKey key;
+            key.value = penalty_of(f, s, c);
+            key.cost = c.cost;
+            key.replicas = c.replicas;
+            key.batch = c.batch;
+            key.acc = c.acc;
+            key.bi = -1;
+            key.ri = a;
+            key.feasible = 1;
+            if (key_better(key, best)) best = key;
         }
     }
-    best = cand_warp_min(best);
-    __shared__ Cand sm[8];
+    best = key_warp_min(best);
+    __shared__ GridKey sm[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) sm[warp] = best;
     __syncthreads();
     if (warp == 0) {
-        Cand c = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : cand_nil();
-        c = cand_warp_min(c);
-        if (lane == 0) store_cand(winners, s, c);
+        GridKey k = sm[0];
+        if (lane > 0 && lane < (int)(blockDim.x >> 5)) k = sm[lane];
+        if (lane >= (int)(blockDim.x >> 5)) k.feasible = 0;
+        k = key_warp_min(k);
+        if (lane == 0) {
+            Cand c = cand_nil();
+            if (k.feasible && k.bi < 0) {
+                c = zero_load_alloc(f, s, k.ri);
+                c.value = penalty_of(f, s, c);
+            } else if (k.feasible) {
+                const int a = k.acc, ri = k.ri, b = k.batch;
+                c.feasible = 1;
+                c.acc = a;
+                c.replicas = k.replicas;
+                c.batch = b;
+                c.cost = k.cost;
+                c.value = k.value;
+                const size_t row = ((size_t)s * f.A + a) * g.R + ri;
+                const long long cell = ((long long)row / g.R * g.B + k.bi) * g.R + ri;
+                const int jl = g.row_j[row];
+                const int K = b + b * f.ratio;
+                if (!g.want_cells && jl != INT_MAX && b >= jl + 2 && K < (1 << 23)) {
+                    // the cell shares its row's chain and was not stored: grid_sort_local's evaluation again
+                    const float lambda = g.rt[s * g.R + ri].y;
+                    ModelStats st;
+                    stats_from_row(g.row_acc[row], g.row_sump[row], b, lambda, st);
+                    const Metrics m = metrics_from(qparams_of(f, s, a), b, st);
+                    c.itl = m.avg_token_time;
+                    c.ttft = m.ttft;
+                    c.rho = m.rho;
+                } else {
+                    c.itl = g.cells.itl[cell];
+                    c.ttft = g.cells.ttft[cell];
+                    c.rho = g.cells.rho[cell];
+                }
+                c.max_rate = __fdiv_rn(rate_max_of((float)g.tab[4 * (g.pair_tab_off[s * f.A + a] + b - 1)]), 1000.0f);
+            }
+            store_cand(winners, s, c);
+        }
     }
 }
 
