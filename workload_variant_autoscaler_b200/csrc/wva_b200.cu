@@ -714,6 +714,7 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
                     tab_len.push_back(Bmax);
                     off += Bmax;
                 }
+        if (off > 0xffffffffll) return h->fail(WVA_ERR_UNSUPPORTED, "grid tables above 2^32 entries");
         const int n_tab = (int)tab_pair.size();
         CK(cudaMemcpyAsync(d_pair_off, pair_tab.data(), sizeof(long long) * std::max(n_pairs, 1), cudaMemcpyHostToDevice,
                            h->stream));
@@ -770,21 +771,26 @@ int prepare_grid(wva_handle* h, const wva_grid* grid, GridPlan* plan) {
     const size_t nc = std::max<size_t>(plan->n_cells, 1);
     // sort workspace: order u32 [n_cells] | items u64 | items_sorted u64 | item counter
     const size_t max_items = (nc + 31) / 32 + (size_t)std::max(plan->n_blocks, 1);
-    const size_t ws = align_up(4 * nc) + 2 * align_up(8 * max_items) + 4 * (2 * kClasses + 32);
+    // ... | per-cell records in global item order (32 x 16 bytes per item)
+    const size_t ws = align_up(4 * nc) + 2 * align_up(8 * max_items) + align_up(4 * (2 * kClasses + 32)) +
+                      align_up(512 * max_items);
     CK(h->d_sort.ensure(ws));
     char* w = (char*)h->d_sort.p;
     g.order = (unsigned*)w;
     g.items = (unsigned long long*)(w + align_up(4 * nc));
     g.items_sorted = (unsigned long long*)(w + align_up(4 * nc) + align_up(8 * max_items));
     g.item_count = (unsigned*)(w + align_up(4 * nc) + 2 * align_up(8 * max_items));
+    g.recs = (uint4*)(w + align_up(4 * nc) + 2 * align_up(8 * max_items) + align_up(4 * (2 * kClasses + 32)));
     h->dbg_plan = g.item_count + 2 * kClasses + 1;
     const size_t n_best = std::max<size_t>((size_t)S * A * R, 1);
     CK(h->d_best.ensure(sizeof(int) * n_best));
     g.best_rank = (int*)h->d_best.p;
-    CK(h->d_rows.ensure((2 * sizeof(double) + sizeof(int)) * n_best + 64));
+    const size_t n_pairs_alloc = std::max<size_t>((size_t)S * A, 1);
+    CK(h->d_rows.ensure(align_up((2 * sizeof(double) + sizeof(int)) * n_best + 64) + 48 * n_pairs_alloc));
     g.row_acc = (double*)h->d_rows.p;
     g.row_sump = g.row_acc + n_best;
     g.row_j = (int*)(g.row_sump + n_best);
+    g.pair_rec = (float4*)((char*)h->d_rows.p + align_up((2 * sizeof(double) + sizeof(int)) * n_best + 64));
     g.Bmax = h->grid_Bmax;
     g.fb_count = (int*)h->d_ctrl.p + CTRL_FB_COUNT;
     g.fb_cap = (int)std::min<size_t>(nc, (size_t)1 << 22);
@@ -833,10 +839,11 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
         grid_sort_local<<<plan.n_blocks, kSortThreads, 0, h->stream>>>(g);
         // one warp per item; the item count lives on the device, so launch for the worst case
         const size_t max_items = (plan.n_cells + 31) / 32 + (size_t)plan.n_blocks;
-        grid_items_scatter<<<(unsigned)((max_items + 255) / 256), 256, 0, h->stream>>>(g);
+        (void)max_items;
+        grid_items_scatter<<<(unsigned)(4 * h->sm_count), 256, 0, h->stream>>>(g);  // warp per item, persistent
         h->launches++;
         CK(cudaEventRecord(h->ev_k0, h->stream));  // wva_last_kernel_ms = the dominant kernel alone
-        const size_t smem = (size_t)kGkWarps * (kGridStash * 32 + kGkTabWin * 4) * sizeof(double);
+        const size_t smem = (size_t)kGkWarps * kGkWarpD * sizeof(double);
         grid_kernel<<<(unsigned)h->sm_count, kGkThreads, smem, h->stream>>>(g);
         h->launches += 2;
     }
@@ -1173,7 +1180,7 @@ int wva_create(wva_handle** out, int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
     cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)((size_t)kGkWarps * (kGridStash * 32 + kGkTabWin * 4) * sizeof(double)));
+                         (int)((size_t)kGkWarps * kGkWarpD * sizeof(double)));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev_k0) != cudaSuccess || cudaEventCreate(&h->ev_k1) != cudaSuccess ||
         cudaEventCreate(&h->ev_d0) != cudaSuccess || cudaEventCreate(&h->ev_d1) != cudaSuccess) {

@@ -155,6 +155,7 @@ enum { kSolveOk = 0, kSolveBail = 1 };
 
 struct ModelStats {  // queuemodel.go:10-19 + mm1kmodel.go:15 + mm1modelstatedependent.go:12
     float throughput, avg_resp_time, avg_wait_time, avg_serv_time, avg_num_in_servers;
+    float tail_rate;  // servRate[N-1] as the solver read it (solve_shared_t only; RateRange.Max follows from it)
 };
 
 // ---------------------------------------------------------------------------
@@ -204,7 +205,13 @@ __device__ long long wva_prof[16];
 // the next window prefetched meanwhile.  Per-lane global loads two steps ahead of their use leave
 // most of the L2 latency exposed (every table entry is its own 32-byte sector): ~160 cycles per head
 // step on an idle SM and 300+ on a busy one, against ~55 from the staged window (tools/head_bench.cu).
+// The FIRST window holds 64 entries (steps 1..64), loaded together with the lane's tail entry and the window
+// constants in one batch at the top of the solve, so a short item (most of them: batch sizes below 64) makes ONE
+// trip to L2 for everything it reads; pass 2 re-uses that window when the whole head fits in it (hmax <= 64).
+// Later windows are 32 entries, prefetched in registers as before.  `tbuf` holds kStagedSlots entries.
 // REV: pairs of checked steps a lane set takes on the per-step path before it returns to the block vote (0 = never returns)
+constexpr int kStagedFirst = 64;   // entries in the first staged window
+constexpr int kStagedSlots = 96;   // slots of tbuf: pass 2 may index up to (hmax - 1) + 31 <= 94 when it re-uses the window
 template <int STASH, int PF = 10, bool STAGED = false, int REV = 1>
 __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st,
                                            double* __restrict__ stash, double* __restrict__ tbuf = nullptr) {
@@ -212,8 +219,28 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     const double lam = (double)lambda;
     const int nh = N - 1;
     Recip A, B;  // reciprocal triples of two consecutive steps (software-pipelined table loads)
+    // staged head: full warp, one table.  Everything the solve reads from the table is requested here in one
+    // batch: the first 64-entry window, the lane's tail entry (T stays in registers for the whole solve) and
+    // entry 0.
+    bool staged = false;
+    int hmax = 0, hmin = 0;
+    double4 win0, win1;
+    Recip T;  // tail entry servRate[N-1]
+    if (STAGED) {
+        staged = warp_mask == 0xffffffffu && __all_sync(0xffffffffu, tab == (const double*)__shfl_sync(0xffffffffu, (unsigned long long)tab, 0));
+        if (staged) {
+            hmax = __reduce_max_sync(0xffffffffu, nh);
+            hmin = __reduce_min_sync(0xffffffffu, nh);
+            const double4* tab4 = reinterpret_cast<const double4*>(tab);
+            const int lane = threadIdx.x & 31;
+            win0 = tab4[min(1 + lane, hmax)];
+            win1 = tab4[min(33 + lane, hmax)];
+        }
+    }
     load_recip(tab, 0, A);
-    const double tail_b = tab[4 * nh];
+    load_recip(tab, nh, T);
+    const double tail_b = T.b;
+    st.tail_rate = (float)tail_b;
     bool bail = !in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail_b, kHiRateLo, kHiRateHi) ||
                 !in_window(A.b, kHiRateLo, kHiRateHi);
     const bool tail_mono = rate_below(lambda, (float)tail_b);
@@ -262,16 +289,6 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     double sum = __dadd_rn(1.0, p);
     int j_end = K + 1;
     if (STASH > 0) stash[0] = p;
-    // staged head: full warp, one table
-    bool staged = false;
-    int hmax = 0, hmin = 0;
-    if (STAGED) {
-        staged = warp_mask == 0xffffffffu && __all_sync(0xffffffffu, tab == (const double*)__shfl_sync(0xffffffffu, (unsigned long long)tab, 0));
-        if (staged) {
-            hmax = __reduce_max_sync(0xffffffffu, nh);
-            hmin = __reduce_min_sync(0xffffffffu, nh);
-        }
-    }
     {
         int n = 1;  // p holds p[n]
         const int n_stop = bail ? 0 : K;
@@ -283,8 +300,6 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             const double4* tab4 = reinterpret_cast<const double4*>(tab);
             double4* tb = reinterpret_cast<double4*>(tbuf);
             const int lane = threadIdx.x & 31;
-            Recip T;
-            load_recip(tab, nh, T);
             bool ok = true;
 #define WVA_SP1_GROUP(SEL, ST)                                                                                    \
     _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                               \
@@ -305,19 +320,27 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         if (ST && n < STASH) stash[n * 32] = p;                                                                   \
         ++n;                                                                                                      \
     }
-#define WVA_SP1(ST)                                                                                               \
-    _Pragma("unroll 1") for (int k = 0; k < 32; k += 4) {                                                         \
+#define WVA_SP1(ST, W)                                                                                            \
+    _Pragma("unroll 1") for (int k = 0; k < (W); k += 4) {                                                        \
+        if (n >= hmax) break; /* every lane is past its head: the pure-tail loops below take over */             \
         if (!__all_sync(0xffffffffu, n + 4 <= n_stop && WVA_FASTWIN(p, blk_lo, blk_span))) { ok = false; break; } \
         if (n + 4 <= hmin) { WVA_SP1_GROUP(false, ST) } else { WVA_SP1_GROUP(true, ST) }                          \
     }
-            double4 nxt = tab4[min(1 + lane, hmax)];  // the next window travels in registers
-            for (int n0 = 1; ok && n0 < hmax; n0 += 32) {
+            // first window: entries 1..64 in slots 0..63 (slot k holds the entry of step 1 + k)
+            __syncwarp();
+            tb[lane] = win0;
+            tb[32 + lane] = win1;
+            __syncwarp();
+            double4 nxt;  // later windows travel in registers
+            if (kStagedFirst + 1 < hmax) nxt = tab4[min(kStagedFirst + 1 + lane, hmax)];
+            if (STASH > 0) { WVA_SP1(true, kStagedFirst) } else { WVA_SP1(false, kStagedFirst) }
+            for (int n0 = kStagedFirst + 1; ok && n0 < hmax; n0 += 32) {
                 WVA_PROF_C(4);
                 __syncwarp();
                 tb[lane] = nxt;
                 __syncwarp();
                 if (n0 + 32 < hmax) nxt = tab4[min(n0 + 32 + lane, hmax)];
-                if (STASH > 0 && n0 < STASH) { WVA_SP1(true) } else { WVA_SP1(false) }
+                WVA_SP1(false, 32)
             }
 #undef WVA_SP1_GROUP
 #undef WVA_SP1
@@ -326,9 +349,12 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
 #ifdef WVA_PROF
         wva_prof[5] = n;
 #endif
-        // invariant at the top of the loop: A = triple of step n, B = triple of step n+1
-        load_recip(tab, n < nh ? n : nh, A);
-        load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
+        // invariant at the top of the loop: A = triple of step n, B = triple of step n+1 (the tail entry is
+        // already in registers: a warp that is past its heads issues no load here)
+        A = T;
+        B = T;
+        if (n < nh) load_recip(tab, n, A);
+        if (n + 1 < nh) load_recip(tab, n + 1, B);
         while (n < n_stop) {
 #define WVA_P1_STEP(R)                                                      \
     p = div_recip(__dmul_rn(p, lam), R);                                    \
@@ -386,13 +412,16 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             if (p == 0.0) { j_end = n + 1; break; }
             if (!(p > 0.0) || hp >= kHiPHi) { bail = true; break; }
             // rare: one step outside the fast loop (exact IEEE division when p is tiny)
-            load_recip(tab, n < nh ? n : nh, A);
+            A = T;
+            if (n < nh) load_recip(tab, n, A);
             p = hp >= kHiPLo ? div_recip(__dmul_rn(p, lam), A) : __ddiv_rn(__dmul_rn(p, lam), A.b);
             sum = __dadd_rn(sum, p);
             if (STASH > 0 && n < STASH) stash[n * 32] = p;
             ++n;
-            load_recip(tab, n < nh ? n : nh, A);
-            load_recip(tab, n + 1 < nh ? n + 1 : nh, B);
+            A = T;
+            B = T;
+            if (n < nh) load_recip(tab, n, A);
+            if (n + 1 < nh) load_recip(tab, n + 1, B);
         }
     }
     __syncwarp(warp_mask);
@@ -462,7 +491,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 // left early: p = p[i] is outside the fast window (tiny or zero): generic loop handles it
             } else if (i < j_end) {
                 // continue the recurrence from the last stashed state: p[i] = step(p[i-1])
-                load_recip(tab, i - 1 < nh ? i - 1 : nh, A);
+                A = T;
+                if (i - 1 < nh) load_recip(tab, i - 1, A);
                 const double pprev = stash[(i - 2) * 32];
                 p = WVA_FASTWIN(pprev, kHiPLo, kHiPHi - kHiPLo) ? div_recip(__dmul_rn(pprev, lam), A)
                                                                  : __ddiv_rn(__dmul_rn(pprev, lam), A.b);
@@ -474,12 +504,13 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             const double4* tab4 = reinterpret_cast<const double4*>(tab);
             double4* tb = reinterpret_cast<double4*>(tbuf);
             const int lane = threadIdx.x & 31;
-            Recip T;
-            load_recip(tab, nh, T);
             bool ok = true;
+            // when the whole head fits in the first window of pass 1 (entry e in slot e - 1) it is still there
+            const bool reuse = hmax <= kStagedFirst;
+            const double4* tbp = tb;
 #define WVA_SP2_GROUP(SEL)                                                                                        \
     _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                               \
-        const double4 e = tb[k + u];                                                                              \
+        const double4 e = tbp[k + u];                                                                             \
         Recip R;                                                                                                  \
         if (SEL) {                                                                                                \
             const bool hd = i < nh;                                                                               \
@@ -509,16 +540,22 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     if (!(SEL)) acc_at_N = acc;
 #define WVA_SP2()                                                                                                 \
     _Pragma("unroll 1") for (int k = 0; k < 32; k += 4) {                                                         \
+        if (i >= hmax) break; /* past every head: the pure-tail loops below take over */                         \
         if (!__all_sync(0xffffffffu, i + 4 <= j_end && WVA_FASTWIN(p, blk2_lo, blk2_span))) { ok = false; break; } \
         if (i + 4 <= hmin) { WVA_SP2_GROUP(false) } else { WVA_SP2_GROUP(true) }                                  \
     }
-            double4 nxt = tab4[min(i + lane, hmax)];
+            double4 nxt;
+            if (!reuse && i < hmax) nxt = tab4[min(i + lane, hmax)];
             for (int i0 = i; ok && i0 < hmax; i0 += 32) {
                 WVA_PROF_C(7);
-                __syncwarp();
-                tb[lane] = nxt;
-                __syncwarp();
-                if (i0 + 32 < hmax) nxt = tab4[min(i0 + 32 + lane, hmax)];
+                if (reuse) {
+                    tbp = tb + (i0 - 1);  // slots up to (hmax - 1) + 31 < kStagedSlots may be touched (values unused)
+                } else {
+                    __syncwarp();
+                    tb[lane] = nxt;
+                    __syncwarp();
+                    if (i0 + 32 < hmax) nxt = tab4[min(i0 + 32 + lane, hmax)];
+                }
                 WVA_SP2()
             }
 #undef WVA_SP2_GROUP
@@ -529,8 +566,10 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         wva_prof[8] = i;
 #endif
         // invariant at the top of the loop: A = triple of the step out of state i, B = of state i+1
-        load_recip(tab, i < nh ? i : nh, A);
-        load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
+        A = T;
+        B = T;
+        if (i < nh) load_recip(tab, i, A);
+        if (i + 1 < nh) load_recip(tab, i + 1, B);
         while (i < j_end) {
 #define WVA_P2_STEP(R)                                                      \
     {                                                                       \
@@ -582,7 +621,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             if (i >= j_end) break;
             if (p == 0.0) { pn = 0.0; break; }
             // rare: tiny p, exact IEEE divisions
-            load_recip(tab, i < nh ? i : nh, A);
+            A = T;
+            if (i < nh) load_recip(tab, i, A);
             pn = __ddiv_rn(p, sum);
             acc = __dadd_rn(acc, __dmul_rn(di, pn));
             di = __dadd_rn(di, 1.0);
@@ -592,8 +632,10 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             }
             p = __ddiv_rn(__dmul_rn(p, lam), A.b);
             ++i;
-            load_recip(tab, i < nh ? i : nh, A);
-            load_recip(tab, i + 1 < nh ? i + 1 : nh, B);
+            A = T;
+            B = T;
+            if (i < nh) load_recip(tab, i, A);
+            if (i + 1 < nh) load_recip(tab, i + 1, B);
         }
     }
     __syncwarp(warp_mask);

@@ -336,6 +336,9 @@ struct GridArgs {
     unsigned* item_count;    // [0] number of items, [1..256] items per class, [257..512] class cursors
     int* best_rank;          // [S*A*R] smallest feasible batch rank (INT_MAX: none)
     CellCols cells;          // internal per-cell columns (ttft, itl, rho always present)
+    float4* pair_rec;        // [S*A][3] per pair: {alpha, beta, gamma, delta}, {in_tok, out_tok (int bits), slo_ttft, slo_itl},
+                             // {min_replicas, tps flag (int bits), 0, 0} -- one 48-byte record instead of ten scattered loads
+    uint4* recs;             // [items][32] per sorted cell: {cell, lambda bits, table entry offset, batch size | pad flag << 31}
     int want_cells;          // 0: the caller did not ask for the cell table -> cells that share their row's chain store
                              // nothing (grid_finalize recomputes the few winners among them); 1: every cell is stored
     int* fb_count;           // cells that need the stored-vector fallback
@@ -510,6 +513,20 @@ __global__ void __launch_bounds__(128) grid_rows(GridArgs g) {
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) {  // the pair's constants as one record (grid_kernel reads it once per item)
+        const int a = sa - s * f.A;
+        const int m = f.srv_model[s];
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m >= 0 && m < f.M) {
+            const int k = m * f.A + a;
+            r0 = make_float4(f.perf_alpha[k], f.perf_beta[k], f.perf_gamma[k], f.perf_delta[k]);
+        }
+        g.pair_rec[3 * sa + 0] = r0;
+        g.pair_rec[3 * sa + 1] = make_float4(__int_as_float(f.srv_in_tokens[s]), __int_as_float(f.srv_out_tokens[s]),
+                                             f.srv_slo_ttft[s], f.srv_slo_itl[s]);
+        g.pair_rec[3 * sa + 2] = make_float4(__int_as_float(f.srv_min_replicas[s]),
+                                             __int_as_float(f.srv_slo_tps[s] > 0.0f ? 1 : 0), 0.f, 0.f);
+    }
     float l2s0 = 0.f, ls_end = 0.f;
     if (toff >= 0) {
         l2s0 = log2f((float)tab[0]);
@@ -826,12 +843,33 @@ __device__ __forceinline__ void grid_items_plan(const GridArgs& g) {
         g.item_count[2 * kClasses + 4] = (unsigned)L;
     }
 }
+// Warp per item: the item takes its place in the global order (class cursors, longest class first) and its
+// cells become 16-byte records in that order — cell id, lambda, the pair's table offset and the batch size —
+// so that grid_kernel fetches an item's operands with ONE coalesced load instead of a chain of dependent ones
+// (queue slot -> item -> order -> batch / replica / pair lists -> rate block).  A partial item (the last of a sort
+// chunk) is padded with copies of its first cell, flagged, so that the whole warp takes part in the staged loads.
 __global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
+    const DevFleet& f = g.f;
     const unsigned n = *g.item_count;
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long it = g.items[i];
-    g.items_sorted[agg_inc(g.item_count + 1 + kClasses, (int)((it >> 40) & 0xff))] = it;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const unsigned long long it = g.items[i];
+        unsigned pos = 0;
+        if (lane == 0) {
+            pos = atomicAdd(g.item_count + 1 + kClasses + (unsigned)((it >> 40) & 0xff), 1u);
+            g.items_sorted[pos] = it;
+        }
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        const bool valid = lane < (unsigned)((it >> 32) & 0xff);
+        const unsigned cell = g.order[(unsigned)it + (valid ? lane : 0u)];
+        int s, a, bi, ri;
+        decode_cell(g, (long long)cell, s, a, bi, ri);
+        const float lambda = g.rt[s * g.R + ri].y;
+        const unsigned toff = (unsigned)g.pair_tab_off[s * f.A + a];
+        const unsigned b = (unsigned)g.batch[bi];
+        g.recs[(size_t)pos * 32 + lane] = make_uint4(cell, __float_as_uint(lambda), toff, b | (valid ? 0u : 0x80000000u));
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -848,54 +886,77 @@ __global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
 // ---------------------------------------------------------------------------
 constexpr int kQLongN = 2 * kClasses + 1, kQLongCtr = kQLongN + 1, kQShortCtr = kQLongN + 2;  // in item_count[]
 
-// An item's operands (decoded cell, table, rates): prepared one item ahead, so that the dependent global
-// loads of the next item are in flight while the current one is being solved.
-struct ItemPrep {
-    unsigned w;
-    long long cell;
-    const double* tab;
-    int s, a, bi, ri, N, K, r;
-    float rmax, lambda;
-    bool valid;
-};
-__device__ __forceinline__ void item_prepare(const GridArgs& g, unsigned w, unsigned lane, ItemPrep& it) {
-    const DevFleet& f = g.f;
-    const unsigned long long item = g.items_sorted[w];
-    // a partial item (the last of a sort chunk) is padded with copies of its first cell so that the
-    // whole warp takes part in the staged table loads; the copies store nothing
-    it.w = w;
-    it.valid = lane < (unsigned)((item >> 32) & 0xff);
-    it.cell = g.order[(unsigned)item + (it.valid ? lane : 0u)];
-    decode_cell(g, it.cell, it.s, it.a, it.bi, it.ri);
-    const int b = g.batch[it.bi];
-    it.r = g.replicas[it.ri];
-    const int pair = it.s * f.A + it.a;
-    it.tab = g.tab + 4 * g.pair_tab_off[pair];
-    it.N = b;
-    it.K = b + b * f.ratio;
-    it.rmax = g.pb[(size_t)g.pair_tab_idx[pair] * g.B + it.bi].x;
-    it.lambda = g.rt[it.s * g.R + it.ri].y;
+// Per-warp shared memory of grid_kernel (doubles): the pass-1 stash, the staged table window, two record slots
+// (the current item's records and the next one's, copied by cp.async while the current item is being solved)
+// and the pair record of the current item.
+constexpr int kGkStashD = kGridStash * 32;              // [state][lane]
+constexpr int kGkTbufD = kStagedSlots * 4;              // staged table entries of 4 doubles
+constexpr int kGkRecD = 2 * 32 * 2;                     // 2 slots x 32 lanes x 16 bytes
+constexpr int kGkPairD = 8;                             // 48-byte pair record (padded to 64)
+constexpr int kGkWarpD = kGkStashD + kGkTbufD + kGkRecD + kGkPairD;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void item_run(const GridArgs& g, const ItemPrep& it, unsigned lane, double* stash_warp, double* tbuf_warp) {
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One item: 32 records (one per lane) already in shared memory.  The solver gets everything it reads from the
+// table in one batch of loads (solve_shared_t STAGED); the pair's constants travel into shared memory by
+// cp.async meanwhile and are read back after the solve, so no operand of the epilogue is held in registers
+// across the solver call and none is fetched by a dependent load afterwards.
+__device__ __forceinline__ void item_run(const GridArgs& g, unsigned w, const uint4 rec, unsigned lane, double* warp_smem) {
     const DevFleet& f = g.f;
-    const unsigned idx = it.w * 32 + lane;
+    double* stash_warp = warp_smem;
+    double* tbuf_warp = warp_smem + kGkStashD;
+    float4* pair_buf = reinterpret_cast<float4*>(warp_smem + kGkStashD + kGkTbufD + kGkRecD);
+    const unsigned idx = w * 32 + lane;
     const long long t_start = g.dbg_cycles ? clock64() : 0;
     unsigned long long t_start_ns = 0;
     if (g.dbg_cycles) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start_ns));
+    const unsigned cell = rec.x;
+    const float lambda = __uint_as_float(rec.y);
+    const double* tab = g.tab + 4 * (size_t)rec.z;
+    const int N = (int)(rec.w & 0x7fffffffu);
+    const bool valid = (rec.w >> 31) == 0;
+    const int K = N + N * f.ratio;
+    const unsigned pair = cell / ((unsigned)g.B * (unsigned)g.R);
+    // one pair per item is the rule (an item is cut from one sort chunk); then lanes 0..2 fetch its record
+    const bool one_pair = __all_sync(0xffffffffu, pair == __shfl_sync(0xffffffffu, pair, 0));
+    __syncwarp();  // the previous item's readers of pair_buf are done
+    if (one_pair && lane < 3) cp_async16(pair_buf + lane, g.pair_rec + 3 * (size_t)pair + lane);
+    cp_async_commit();
     ModelStats st;
     WVA_PROF_T(10);
-    const int rc = solve_shared_t<kGridStash, 10, true>(it.tab, it.N, it.K, it.lambda, st, stash_warp + lane, tbuf_warp);
+    const int rc = solve_shared_t<kGridStash, 10, true>(tab, N, K, lambda, st, stash_warp + lane, tbuf_warp);
     WVA_PROF_T(11);
-    if (it.valid) {
+    cp_async_wait<0>();
+    __syncwarp();
+    if (valid) {
         if (rc != kSolveOk) {
             const int k = atomicAdd(g.fb_count, 1);
-            if (k < g.fb_cap) g.fb_cells[k] = it.cell;
+            if (k < g.fb_cap) g.fb_cells[k] = (long long)cell;
         } else {
-            const QParams q = qparams_of(f, it.s, it.a);
-            const Metrics m = metrics_from(q, it.N, st);
-            const bool feas = cell_feasible(feas_row(f, it.s, it.rmax), it.r, it.lambda, m);
-            store_cell(g, it.cell, 1, feas ? 1 : 0, m);
-            if (feas) atomicMin(&g.best_rank[((size_t)it.s * f.A + it.a) * g.R + it.ri], g.batch_rank[it.bi]);
+            const float4 r0 = one_pair ? pair_buf[0] : g.pair_rec[3 * (size_t)pair + 0];
+            const float4 r1 = one_pair ? pair_buf[1] : g.pair_rec[3 * (size_t)pair + 1];
+            const float4 r2 = one_pair ? pair_buf[2] : g.pair_rec[3 * (size_t)pair + 2];
+            QParams q;
+            q.alpha = r0.x; q.beta = r0.y; q.gamma = r0.z; q.delta = r0.w;
+            q.in_tok = __float_as_int(r1.x); q.out_tok = __float_as_int(r1.y);
+            FeasRow fr;
+            fr.slo_ttft = r1.z;
+            fr.slo_itl = r1.w;
+            fr.min_replicas = __float_as_int(r2.x);
+            fr.tps = __float_as_int(r2.y) != 0;
+            fr.lim = feas_lim(rate_max_of(st.tail_rate));  // RateRange.Max of (pair, N) from servRate[N-1]
+            int s, a, bi, ri;
+            decode_cell(g, (long long)cell, s, a, bi, ri);
+            const Metrics m = metrics_from(q, N, st);
+            const bool feas = cell_feasible(fr, g.replicas[ri], lambda, m);
+            store_cell(g, (long long)cell, 1, feas ? 1 : 0, m);
+            if (feas) atomicMin(&g.best_rank[(size_t)pair * g.R + ri], g.batch_rank[bi]);
             if (g.dbg_cycles) {
                 g.dbg_cycles[idx] = (unsigned)(clock64() - t_start);
                 if (lane < 3) {  // timeline: [0] start ns, [1] SM id, [2] end ns (low 32 bits of %globaltimer)
@@ -911,18 +972,12 @@ __device__ __forceinline__ void item_run(const GridArgs& g, const ItemPrep& it, 
     __syncwarp();
     WVA_PROF_T(14);
 }
-__device__ __forceinline__ void grid_item(const GridArgs& g, unsigned w, unsigned lane, double* stash_warp, double* tbuf_warp) {
-    ItemPrep it;
-    WVA_PROF_T(9);
-    item_prepare(g, w, lane, it);
-    item_run(g, it, lane, stash_warp, tbuf_warp);
-}
 
 __global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
-    extern __shared__ double grid_stash[];  // [warp][state][lane]
+    extern __shared__ double grid_smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* stash_warp = grid_stash + (size_t)warp * (kGridStash * 32 + kGkTabWin * 4);
-    double* tbuf_warp = stash_warp + kGridStash * 32;  // 32 table entries of 4 doubles
+    double* warp_smem = grid_smem + (size_t)warp * kGkWarpD;
+    uint4* rec_slot = reinterpret_cast<uint4*>(warp_smem + kGkStashD + kGkTbufD);  // [2][32]
     const unsigned n_items = g.item_count[0], n_long = g.item_count[kQLongN];
     const bool sub0 = (warp & 3) == 0;
     // the long items are spread over as few CTAs as possible (long_per_sm per CTA): the other CTAs keep all
@@ -942,21 +997,37 @@ __global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
             if (lane == 0) w = atomicAdd(g.item_count + kQLongCtr, 1u);
             w = __shfl_sync(0xffffffffu, w, 0);
             if (w >= n_long) break;
-            grid_item(g, w, lane, stash_warp, tbuf_warp);
+            const uint4 rec = g.recs[(size_t)w * 32 + lane];
+            item_run(g, w, rec, lane, warp_smem);
         }
         if (n_parked > 0) asm volatile("bar.arrive 1, %0;" ::"r"(bar_threads) : "memory");
     } else if (sub0 && my_long > 0 && !long_warp && (int)(warp >> 2) >= my_long + g.long_share) {
         asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
     }
-    // short queue.  (Pulling and preparing the next item before solving the current one was measured:
-    // the operands kept live across the solver call cost it registers and the 16-step loops slowed
-    // from 46 to 57 cycles per state.)
-    for (;;) {
-        unsigned w = 0;
-        if (lane == 0) w = atomicAdd(g.item_count + kQShortCtr, 1u);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= n_items) break;
-        grid_item(g, w, lane, stash_warp, tbuf_warp);
+    // short queue, software-pipelined two items deep: while item k is being solved, the records of item k + 1
+    // travel into the other record slot (cp.async: no registers) and the queue slot of item k + 2 is being
+    // fetched (one register in lane 0).  At the top of an iteration everything the solver needs is one
+    // shared-memory read away.
+    unsigned w_cur = 0, w_nxt = 0;
+    if (lane == 0) {
+        w_cur = atomicAdd(g.item_count + kQShortCtr, 2u);
+        w_nxt = w_cur + 1;
+    }
+    w_cur = __shfl_sync(0xffffffffu, w_cur, 0);
+    w_nxt = __shfl_sync(0xffffffffu, w_nxt, 0);
+    if (w_cur < n_items) cp_async16(rec_slot + lane, g.recs + (size_t)w_cur * 32 + lane);
+    cp_async_commit();
+    for (unsigned k = 0;; ++k) {
+        if (w_cur >= n_items) break;
+        if (w_nxt < n_items) cp_async16(rec_slot + 32 * ((k + 1) & 1) + lane, g.recs + (size_t)w_nxt * 32 + lane);
+        cp_async_commit();
+        unsigned w_nn = 0;
+        if (lane == 0) w_nn = atomicAdd(g.item_count + kQShortCtr, 1u);
+        cp_async_wait<1>();  // all but the newest group: this item's records have landed (each lane reads its own)
+        const uint4 rec = rec_slot[32 * (k & 1) + lane];
+        item_run(g, w_cur, rec, lane, warp_smem);
+        w_cur = w_nxt;
+        w_nxt = __shfl_sync(0xffffffffu, w_nn, 0);
     }
 }
 
