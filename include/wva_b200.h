@@ -228,6 +228,16 @@ int wva_solve(wva_handle *h, const wva_fleet *fleet, wva_allocs *candidates,
 int wva_grid_solve(wva_handle *h, const wva_fleet *fleet, const wva_grid *grid,
                    wva_cells *cells, wva_allocs *winners);
 
+/*
+ * Solver.SolveGreedy + the best-effort saturation policies (pkg/solver/greedy.go:35-341) over a candidate
+ * table the caller already holds: `candidates` (S*A, value = transition penalty as wva_analyze returns it) is
+ * read, and modified where the reference scales best-effort allocations; `winners` (S) is written.  Host only
+ * (no handle, no device work).  The multi-GPU limited mode shards candidate generation over the ranks,
+ * all-gathers the candidate tables and calls this on every rank: the greedy pass is one
+ * sequential walk over a shared capacity map and does not shard.
+ */
+int wva_solve_greedy(const wva_fleet *fleet, wva_allocs *candidates, wva_allocs *winners);
+
 /* Latency sweep of QueueAnalyzer.Analyze over n_rates rates per (server, acc). */
 int wva_sweep(wva_handle *h, const wva_fleet *fleet, int32_t n_rates, wva_sweep_out *out);
 

@@ -73,6 +73,25 @@ def test_best_effort_policies_allocate_more(oracle_mod):
     assert (rr["feasible"] & (rr["acc"] >= 0)).sum() >= n0
 
 
+@pytest.mark.parametrize("policy", [SAT_NONE, SAT_PRIORITY_EXHAUSTIVE, SAT_PRIORITY_ROUND_ROBIN, SAT_ROUND_ROBIN])
+@pytest.mark.parametrize("delayed", [False, True])
+@pytest.mark.parametrize("cap", [6, 25, 1 << 20])
+def test_product_greedy_on_host_matches_oracle(oracle_mod, policy, delayed, cap):
+    """The library's SolveGreedy (wva_solve_greedy: host C++, no device) over the oracle's candidate table equals
+    the oracle's SolveGreedy — the product's greedy pass itself is checked on the CPU box."""
+    from workload_variant_autoscaler_b200 import Allocs, greedy_solve
+    from workload_variant_autoscaler_b200._abi import ALLOC_COLUMNS
+    f = limited_fleet(13 + cap % 7, cap, policy, delayed)
+    cand0 = oracle_mod.calculate(f)
+    cand_o, win_o = oracle_mod.solve(f, cand0)
+    cand = Allocs(f.n_servers * f.n_acc)
+    for name, _ in ALLOC_COLUMNS:
+        getattr(cand, name)[:] = cand0.reshape(-1)[name]
+    cand_g, win_g = greedy_solve(f, cand)
+    assert_allocs_equal(win_g, win_o, f"greedy winners policy={policy} delayed={delayed} cap={cap}")
+    assert_allocs_equal(cand_g, cand_o, "greedy candidates (after best-effort scaling)")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("policy", [SAT_NONE, SAT_PRIORITY_EXHAUSTIVE, SAT_PRIORITY_ROUND_ROBIN, SAT_ROUND_ROBIN])
 @pytest.mark.parametrize("delayed", [False, True])

@@ -13,7 +13,7 @@ from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libwva_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("wva_b200.cu", "wva_kernels.cuh", "wva_device.cuh")]
+SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("wva_b200.cu", "wva_kernels.cuh", "wva_device.cuh", "wva_size.cuh")]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "wva_b200.h")
 
 NVCC_FLAGS = [
@@ -38,7 +38,7 @@ EXPORTS = (
     "wva_tunables_default", "wva_create", "wva_destroy", "wva_strerror", "wva_last_error", "wva_abi_version",
     "wva_analyze", "wva_solve", "wva_grid_solve", "wva_sweep", "wva_upload", "wva_update_load", "wva_resolve",
     "wva_grid_solve_device", "wva_resolve_device", "wva_stream", "wva_synchronize", "wva_launch_count",
-    "wva_last_kernel_ms", "wva_last_device_ms", "wva_summarize",
+    "wva_last_kernel_ms", "wva_last_device_ms", "wva_summarize", "wva_solve_greedy",
     "wva_xchg_create", "wva_xchg_open", "wva_xchg_publish", "wva_xchg_error", "wva_xchg_destroy",
 )
 
@@ -75,6 +75,7 @@ def lib():
         ("wva_grid_solve_device", [vp, C.POINTER(_abi.GridC), C.POINTER(_abi.AllocsC)]),
         ("wva_resolve_device", [vp, C.POINTER(_abi.AllocsC)]),
         ("wva_synchronize", [vp]),
+        ("wva_solve_greedy", [C.POINTER(_abi.FleetC), C.POINTER(_abi.AllocsC), C.POINTER(_abi.AllocsC)]),
         ("wva_summarize", [vp, C.POINTER(_abi.SummaryC)]),
         ("wva_xchg_create", [vp, C.c_int, C.c_int, C.c_size_t, C.c_void_p]),
         ("wva_xchg_open", [vp, C.c_int, C.c_void_p]),

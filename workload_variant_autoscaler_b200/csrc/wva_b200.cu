@@ -19,6 +19,7 @@
 
 #include "../../include/wva_b200.h"
 #include "wva_kernels.cuh"
+#include "wva_size.cuh"
 
 using namespace wva;
 
@@ -251,27 +252,29 @@ AllocCols cols_from_abi(const wva_allocs* a) {
 }
 
 // ---- fleet validation + upload ----------------------------------------------
-int validate_fleet(wva_handle* h, const wva_fleet* f) {
-    if (!f) return h->fail(WVA_ERR_BAD_ARG, "fleet is NULL");
-    if (f->n_acc < 0 || f->n_types < 0 || f->n_models < 0 || f->n_servers < 0)
-        return h->fail(WVA_ERR_BAD_ARG, "negative size in fleet");
+// nullptr when the fleet is well formed, else what is wrong with it
+const char* fleet_problem(const wva_fleet* f) {
+    if (!f) return "fleet is NULL";
+    if (f->n_acc < 0 || f->n_types < 0 || f->n_models < 0 || f->n_servers < 0) return "negative size in fleet";
     const bool need_a = f->n_acc > 0, need_t = f->n_types > 0, need_ma = f->n_models > 0 && f->n_acc > 0,
                need_s = f->n_servers > 0;
-    if (need_a && (!f->acc_cost || !f->acc_multiplicity || !f->acc_type))
-        return h->fail(WVA_ERR_BAD_ARG, "NULL accelerator column");
-    if (need_t && !f->type_capacity) return h->fail(WVA_ERR_BAD_ARG, "NULL capacity column");
+    if (need_a && (!f->acc_cost || !f->acc_multiplicity || !f->acc_type)) return "NULL accelerator column";
+    if (need_t && !f->type_capacity) return "NULL capacity column";
     if (need_ma && (!f->perf_present || !f->perf_alpha || !f->perf_beta || !f->perf_gamma || !f->perf_delta ||
                     !f->perf_acc_count || !f->perf_max_batch || !f->perf_at_tokens))
-        return h->fail(WVA_ERR_BAD_ARG, "NULL perf column");
+        return "NULL perf column";
     if (need_s && (!f->srv_model || !f->srv_priority || !f->srv_has_target || !f->srv_slo_itl || !f->srv_slo_ttft ||
                    !f->srv_slo_tps || !f->srv_keep_acc || !f->srv_min_replicas || !f->srv_max_batch ||
                    !f->srv_arrival_rpm || !f->srv_in_tokens || !f->srv_out_tokens || !f->srv_cur_acc ||
                    !f->srv_cur_replicas || !f->srv_cur_cost))
-        return h->fail(WVA_ERR_BAD_ARG, "NULL server column");
+        return "NULL server column";
     for (int a = 0; a < f->n_acc; ++a)
-        if (f->n_types > 0 && (f->acc_type[a] < 0 || f->acc_type[a] >= f->n_types))
-            return h->fail(WVA_ERR_BAD_ARG, "accelerator type id out of range");
-    if (f->tun.max_queue_to_batch_ratio < 0) return h->fail(WVA_ERR_BAD_ARG, "negative queue ratio");
+        if (f->n_types > 0 && (f->acc_type[a] < 0 || f->acc_type[a] >= f->n_types)) return "accelerator type id out of range";
+    if (f->tun.max_queue_to_batch_ratio < 0) return "negative queue ratio";
+    return nullptr;
+}
+int validate_fleet(wva_handle* h, const wva_fleet* f) {
+    if (const char* what = fleet_problem(f)) return h->fail(WVA_ERR_BAD_ARG, what);
     return WVA_OK;
 }
 
@@ -288,11 +291,8 @@ Column place(std::vector<std::pair<Column, const void*>>& plan, size_t& off, con
     return c;
 }
 
-int upload_fleet(wva_handle* h, const wva_fleet* f) {
-    int rc = validate_fleet(h, f);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(h->stream));  // the pinned stage may still feed an earlier async copy
-    HostFleet& hf = h->hf;
+// Host copy of every column (the caller's pointers are never retained).
+void fill_host_fleet(HostFleet& hf, const wva_fleet* f) {
     const size_t A = f->n_acc, T = f->n_types, M = f->n_models, S = f->n_servers;
     hf.A = (int)A; hf.T = (int)T; hf.M = (int)M; hf.S = (int)S;
     copy_col(hf.acc_cost, f->acc_cost, A);
@@ -326,6 +326,14 @@ int upload_fleet(wva_handle* h, const wva_fleet* f) {
     hf.delayed_best_effort = f->delayed_best_effort != 0;
     hf.saturation_policy = f->saturation_policy;
     hf.tun = f->tun;
+}
+
+int upload_fleet(wva_handle* h, const wva_fleet* f) {
+    int rc = validate_fleet(h, f);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));  // the pinned stage may still feed an earlier async copy
+    HostFleet& hf = h->hf;
+    fill_host_fleet(hf, f);
 
     // one arena, one H2D copy; the three load columns are adjacent so that
     // wva_update_load moves a single contiguous range
@@ -463,80 +471,93 @@ int prepare_size(wva_handle* h) {
     return WVA_OK;
 }
 
-// Round-based K1: see the comment above SzArgs in wva_kernels.cuh.
+// Round-based K1 with speculative bisection trees: see the comment at the top of wva_size.cuh.
+int size_depth_for(int n) {
+    int d = n <= 2048 ? 5 : (n <= 8192 ? 4 : (n <= 40000 ? 3 : 2));
+    if (const char* e = getenv("WVA_SIZE_DEPTH")) d = atoi(e);
+    return std::min(std::max(d, 1), kSzMaxDepth);
+}
 int run_size_rounds(wva_handle* h, const SizeArgs& sa, int n) {
+    const int D = size_depth_for(n);
+    const size_t per_cand = 2 * ((size_t)(1 << D) - 1 + 2);  // two searches: a tree each, plus the two end points
+    const size_t cap = per_cand * (size_t)n;                 // requests per round, worst case
     const size_t n2 = 2 * (size_t)n;
     // state block
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 16); return at; };
-    const size_t o_xmin = take(4 * n2), o_xmax = take(4 * n2), o_y0 = take(4 * n2), o_y1 = take(4 * n2), o_xs = take(4 * n2);
+    const size_t o_xmin = take(4 * n2), o_xmax = take(4 * n2), o_xs = take(4 * n2);
     const size_t o_sst = take(n2), o_inc = take(n2), o_iter = take(n2), o_ind = take(n2), o_slot = take(4 * n2);
     const size_t o_phase = take(n), o_rmax = take(4 * (size_t)n), o_l2s0 = take(4 * (size_t)n), o_l2sN = take(4 * (size_t)n),
-                 o_lsN = take(4 * (size_t)n), o_rstar = take(4 * (size_t)n), o_total = take(4 * (size_t)n),
-                 o_cost = take(4 * (size_t)n), o_nrep = take(8 * (size_t)n);
+                 o_lsN = take(4 * (size_t)n), o_rstar = take(4 * (size_t)n), o_cost = take(4 * (size_t)n),
+                 o_nrep = take(8 * (size_t)n), o_aslot = take(4 * (size_t)n);
     CK(h->d_sz_state.ensure(o));
     char* sp = (char*)h->d_sz_state.p;
-    // request block (capacity 2n)
+    // request block
     o = 0;
-    const size_t r_id = take(4 * n2), r_lam = take(4 * n2), r_key = take(n2), r_out = take(16 * n2), r_bail = take(n2),
+    const size_t r_id = take(4 * cap), r_lam = take(4 * cap), r_key = take(cap), r_out = take(16 * cap), r_bail = take(cap),
                  r_cnt = take(16);
     CK(h->d_sz_req.ensure(o));
     char* rp = (char*)h->d_sz_req.p;
     // sort workspace
-    const size_t chunks = (n2 + kSortChunk - 1) / kSortChunk;
-    const size_t max_items = (n2 + 31) / 32 + chunks;
+    const size_t chunks = (cap + kSortChunk - 1) / kSortChunk;
+    const size_t max_items = (cap + 31) / 32 + chunks;
     o = 0;
-    const size_t w_order = take(4 * n2), w_items = take(8 * max_items), w_sorted = take(8 * max_items),
+    const size_t w_order = take(4 * cap), w_items = take(8 * max_items), w_sorted = take(8 * max_items),
                  w_cnt = take(4 * (2 * kClasses + 8));
     CK(h->d_sz_sort.ensure(o));
     char* wp = (char*)h->d_sz_sort.p;
     CK(h->sz_pin.ensure(64));
 
-    SzArgs g{};
+    Sz2Args g{};
     g.f = sa.f;
     g.cand_pair = sa.cand_pair;
     g.cand_N = sa.cand_N;
     g.n_cand = n;
+    g.depth = D;
     g.tab = (const double*)h->d_sz_tab.p;
     g.tab_off = (const long long*)h->d_sz_off.p;
     g.ls = (const float*)h->d_sz_ls.p;
-    g.xmin = (float*)(sp + o_xmin); g.xmax = (float*)(sp + o_xmax); g.y0 = (float*)(sp + o_y0); g.y1 = (float*)(sp + o_y1);
-    g.xs = (float*)(sp + o_xs);
+    g.xmin = (float*)(sp + o_xmin); g.xmax = (float*)(sp + o_xmax); g.xs = (float*)(sp + o_xs);
     g.sst = (uint8_t*)(sp + o_sst); g.inc = (uint8_t*)(sp + o_inc); g.iter = (uint8_t*)(sp + o_iter);
     g.ind = (int8_t*)(sp + o_ind); g.slot = (int*)(sp + o_slot);
     g.phase = (uint8_t*)(sp + o_phase);
     g.rmax = (float*)(sp + o_rmax); g.l2s0 = (float*)(sp + o_l2s0); g.l2sN = (float*)(sp + o_l2sN); g.lsN = (float*)(sp + o_lsN);
-    g.rate_star = (float*)(sp + o_rstar); g.total_rate = (float*)(sp + o_total); g.cost = (float*)(sp + o_cost);
+    g.rate_star = (float*)(sp + o_rstar); g.cost = (float*)(sp + o_cost);
     g.nrep = (long long*)(sp + o_nrep);
+    g.aslot = (int*)(sp + o_aslot);
     g.req_id = (unsigned*)(rp + r_id); g.req_lam = (float*)(rp + r_lam); g.req_key = (uint8_t*)(rp + r_key);
-    g.req_out = (float4*)(rp + r_out); g.req_bail = (uint8_t*)(rp + r_bail); g.n_req = (unsigned*)(rp + r_cnt);
+    g.req_out = (float4*)(rp + r_out); g.req_bail = (uint8_t*)(rp + r_bail);
+    g.n_req = (unsigned*)(rp + r_cnt); g.n_live = g.n_req + 1;
     g.ws.order = (unsigned*)(wp + w_order); g.ws.items = (unsigned long long*)(wp + w_items);
     g.ws.items_sorted = (unsigned long long*)(wp + w_sorted); g.ws.item_count = (unsigned*)(wp + w_cnt);
     g.cand = sa.cand;
     g.fb_count = sa.fb_count; g.fb_list = sa.fb_list; g.fb_cap = sa.fb_cap;
 
     const unsigned nb = (unsigned)((n + 255) / 256);
-    sz_init<<<nb, 256, 0, h->stream>>>(g);
+    const unsigned cks = (unsigned)chunks, items_blocks = (unsigned)((max_items + 255) / 256),
+                   solve_blocks = (unsigned)((max_items * 32 + 255) / 256);
+    sz2_init<<<nb, 256, 0, h->stream>>>(g);
     h->launches++;
     unsigned* pin = (unsigned*)h->sz_pin.p;
-    // at most 1 + 102 evaluations per search, then two Analyze rounds, then the final consume
-    for (int round = 0; round < 112; ++round) {
-        CK(cudaMemsetAsync(g.n_req, 0, sizeof(unsigned), h->stream));
-        CK(cudaMemsetAsync(g.ws.item_count, 0, sizeof(unsigned) * (2 * kClasses + 1), h->stream));
-        sz_advance<<<nb, 256, 0, h->stream>>>(g);
-        h->launches++;
-        // the request count decides whether another round is needed
-        CK(cudaMemcpyAsync(pin, g.n_req, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    // Rounds are enqueued in groups without looking at the device: every kernel of a round leaves at once when the
+    // round has no requests, so over-launching costs microseconds while a host round trip per round costs more.
+    // A search needs 1 + ceil(100 / D) rounds at most, then two Analyze rounds and the final consume.
+    const int max_rounds = 1 + (100 + D - 1) / D + 4;
+    const int group = 4;
+    for (int round = 0; round < max_rounds; round += group) {
+        for (int r = 0; r < group; ++r) {
+            sz2_round_reset<<<3, 256, 0, h->stream>>>(g);
+            sz2_advance<<<nb, 256, 0, h->stream>>>(g);
+            sz2_sort_local<<<cks, kSortThreads, 0, h->stream>>>(g);
+            ws_items_scan<<<1, 256, 0, h->stream>>>(g.ws);
+            ws_items_scatter<<<items_blocks, 256, 0, h->stream>>>(g.ws);
+            sz2_solve<<<solve_blocks, 256, 0, h->stream>>>(g);
+            h->launches += 6;
+        }
+        // candidates still unfinished after the group's last advance decide whether another group is needed
+        CK(cudaMemcpyAsync(pin, g.n_live, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        const unsigned n_req = *pin;
-        if (n_req == 0) break;
-        const unsigned cks = (n_req + kSortChunk - 1) / kSortChunk;
-        const unsigned items_max = (n_req + 31) / 32 + cks;
-        sz_sort_local<<<cks, kSortThreads, 0, h->stream>>>(g);
-        ws_items_scan<<<1, 256, 0, h->stream>>>(g.ws);
-        ws_items_scatter<<<(items_max + 255) / 256, 256, 0, h->stream>>>(g.ws);
-        sz_solve<<<(items_max * 32 + 255) / 256, 256, 0, h->stream>>>(g);
-        h->launches += 4;
+        if (*pin == 0) break;
     }
     CK(cudaGetLastError());
     return WVA_OK;
@@ -1098,6 +1119,25 @@ void cands_to_abi(const std::vector<HostCand>& v, wva_allocs* out) {
     }
 }
 
+bool abi_to_cands(const wva_allocs* in, size_t n, std::vector<HostCand>& out) {
+    if (!in || (n && (!in->feasible || !in->acc || !in->replicas || !in->cost || !in->value))) return false;
+    out.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        HostCand& c = out[i];
+        c.feasible = in->feasible[i];
+        c.acc = in->acc[i];
+        c.replicas = in->replicas[i];
+        c.batch = in->batch ? in->batch[i] : 0;
+        c.cost = in->cost[i];
+        c.value = in->value[i];
+        c.itl = in->itl ? in->itl[i] : 0.0f;
+        c.ttft = in->ttft ? in->ttft[i] : 0.0f;
+        c.rho = in->rho ? in->rho[i] : 0.0f;
+        c.max_rate = in->max_rate ? in->max_rate[i] : 0.0f;
+    }
+    return true;
+}
+
 // resident analyze + greedy solve with host outputs
 int run_greedy_host(wva_handle* h, wva_allocs* candidates, wva_allocs* winners) {
     const HostFleet& hf = h->hf;
@@ -1394,6 +1434,22 @@ int wva_analyze(wva_handle* h, const wva_fleet* fleet, wva_allocs* candidates) {
     // kernel into a scratch winner block so that candidate values are final
     wva_allocs dummy{};
     return run_size_host(h, candidates, &dummy);
+}
+
+// SolveGreedy + best-effort policies over a candidate table the caller already holds (host only, no device work):
+// the multi-GPU limited mode all-gathers the per-shard candidate tables and runs this redundantly on every rank.
+int wva_solve_greedy(const wva_fleet* fleet, wva_allocs* candidates, wva_allocs* winners) {
+    if (fleet_problem(fleet) || !winners) return WVA_ERR_BAD_ARG;
+    HostFleet hf;
+    fill_host_fleet(hf, fleet);
+    for (int a = 0; a < hf.A; ++a)
+        if (hf.T <= 0 || hf.acc_type[a] < 0 || hf.acc_type[a] >= hf.T) return WVA_ERR_BAD_ARG;
+    std::vector<HostCand> cand, win((size_t)hf.S);
+    if (!abi_to_cands(candidates, (size_t)hf.S * hf.A, cand)) return WVA_ERR_BAD_ARG;
+    GreedySolver(hf, cand, win).run();
+    cands_to_abi(cand, candidates);
+    cands_to_abi(win, winners);
+    return WVA_OK;
 }
 
 int wva_resolve(wva_handle* h, wva_allocs* candidates, wva_allocs* winners) {

@@ -5,7 +5,8 @@
 //                       sort, persistent warps pulling 32-cell items, fused feasibility + batch-rank minimum
 //   grid_fallback       stored-vector re-run of the rare cells the streaming solve bails on
 //   grid_finalize  K3   per-server argmin over partials (warp shuffle -> smem -> record)
-//   sz_* kernels   K1   CreateAllocation per (server, acc) candidate as rounds of sorted solve batches
+//   sz2_* kernels  K1   (wva_size.cuh) CreateAllocation per (server, acc) candidate as rounds of sorted solve
+//                       batches with speculative bisection trees
 //   size_fallback       stored-vector re-run of candidates that bailed
 //   trivial_kernel      nil / zero-load candidates
 //   unlimited_kernel    Server.Calculate value + SolveUnlimited argmin per server
@@ -1355,16 +1356,8 @@ __global__ void size_fallback(SizeArgs g, double* scratch, size_t slot_doubles, 
 }
 
 // ---------------------------------------------------------------------------
-// K1, round-based: CreateAllocation for every candidate as a sequence of SOLVE BATCHES.
-//
-// The reference runs, per candidate, two sequential bisections (utils.go:26-70) of <= 102
-// model solves each, then two Analyze calls.  Here every candidate is a small state machine
-// (sz_advance) that emits at most two solve requests per round (one per bisection, later one
-// per Analyze); all requests of a round are ordered by estimated chain length (same counting
-// sort as the grid) and solved 32-per-warp by sz_solve with the shared-table solver; the
-// next round consumes the results.  Same arithmetic, same sequence of lambda values per
-// candidate, so results are bit-identical — but the GPU always works on warps of
-// equal-length chains instead of one thread walking a whole bisection.
+// K1 (size candidates as rounds of sorted solve batches) lives in wva_size.cuh; the sort workspace and the
+// item ordering kernels it shares with nothing else stay here next to the grid's.
 // ---------------------------------------------------------------------------
 struct SortWs {
     unsigned* order;
@@ -1372,267 +1365,7 @@ struct SortWs {
     unsigned long long* items_sorted;
     unsigned* item_count;  // [0] items, [1..256] per class, [257..512] cursors
 };
-enum { SZ_START = 0, SZ_WAIT_Y0 = 1, SZ_WAIT_Y1 = 2, SZ_WAIT_ITER = 3, SZ_DONE = 4, SZ_OFF = 5 };
 enum { PH_SEARCH = 0, PH_WAIT_STAR = 1, PH_WAIT_FINAL = 2, PH_DONE = 3, PH_NIL = 4, PH_BAIL = 5 };
-struct SzArgs {
-    DevFleet f;
-    const int* cand_pair;  // [n] pair ids, descending N
-    const int* cand_N;     // [n]
-    int n_cand;
-    const double* tab;     // shared-format tables, one per candidate
-    const long long* tab_off;  // [n]
-    const float* ls;
-    // search state, index 2*j + which (0: TTFT, 1: ITL)
-    float *xmin, *xmax, *y0, *y1, *xs;
-    uint8_t *sst, *inc, *iter;
-    int8_t* ind;
-    int* slot;             // [2n] request slot this round (-1: none)
-    // candidate state
-    uint8_t* phase;
-    float *rmax, *l2s0, *l2sN, *lsN, *rate_star, *total_rate, *cost;
-    long long* nrep;
-    // requests of the current round
-    unsigned* req_id;      // 4*j + kind (0 TTFT eval, 1 ITL eval, 2 Analyze(lambda*), 3 Analyze(final))
-    float* req_lam;
-    uint8_t* req_key;
-    float4* req_out;       // kinds 0/1: x = y; kinds 2/3: throughput, ttft, itl, rho
-    uint8_t* req_bail;
-    unsigned* n_req;       // device counter
-    SortWs ws;
-    AllocCols cand;
-    int* fb_count;
-    int* fb_list;
-    int fb_cap;
-};
-
-__device__ __forceinline__ unsigned agg_alloc(unsigned* counter) {  // warp-aggregated slot allocation
-    const unsigned act = __activemask();
-    const int leader = __ffs(act) - 1, lane = threadIdx.x & 31;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(act));
-    base = __shfl_sync(act, base, leader);
-    return base + __popc(act & ((1u << lane) - 1u));
-}
-
-__device__ __forceinline__ void sz_emit(const SzArgs& g, int j, int kind, float lambda, int slot_idx) {
-    const unsigned slot = agg_alloc(g.n_req);
-    g.req_id[slot] = (unsigned)j * 4u + (unsigned)kind;
-    g.req_lam[slot] = lambda;
-    const int N = g.cand_N[j], K = N + N * g.f.ratio;
-    const long long off = g.tab_off[j];
-    g.req_key[slot] = (uint8_t)length_class(estimate_len(g.tab + 4 * off, g.ls + off + j, N, K, lambda, log2f(lambda),
-                                                         g.l2s0[j], g.l2sN[j], g.lsN[j]));
-    g.slot[slot_idx] = (int)slot;
-}
-
-__global__ void __launch_bounds__(256) sz_init(SzArgs g) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= g.n_cand) return;
-    const DevFleet& f = g.f;
-    const int pair = g.cand_pair[j], s = pair / f.A;
-    const int N = g.cand_N[j], K = N + N * f.ratio;
-    const double* tab = g.tab + 4 * g.tab_off[j];
-    const float s1 = (float)tab[0], sN = (float)tab[4 * (N - 1)];
-    const float rmin = rate_min_of(s1), rmax = rate_max_of(sN);
-    g.rmax[j] = rmax;
-    g.l2s0[j] = log2f(s1);
-    g.l2sN[j] = log2f(sN);
-    g.lsN[j] = (g.ls + g.tab_off[j] + j)[N - 1];
-    const float slo_ttft = f.srv_slo_ttft[s], slo_itl = f.srv_slo_itl[s], slo_tps = f.srv_slo_tps[s];
-    uint8_t ph = PH_SEARCH;
-    // K <= 1: the model is never valid (queuemodel.go:31); negative targets: TargetPerf.check :322-329
-    if (K < 2 || slo_itl < 0.0f || slo_ttft < 0.0f || slo_tps < 0.0f) ph = PH_NIL;
-    g.phase[j] = ph;
-    const float lmin = __fdiv_rn(rmin, 1000.0f), lmax = __fdiv_rn(rmax, 1000.0f);
-    for (int w = 0; w < 2; ++w) {
-        const float target = w == 0 ? slo_ttft : slo_itl;
-        g.xmin[2 * j + w] = lmin;
-        g.xmax[2 * j + w] = lmax;
-        g.xs[2 * j + w] = lmax;  // lambdaStar when the target is disabled (queueanalyzer.go:205,218)
-        g.sst[2 * j + w] = target > 0.0f ? SZ_START : SZ_OFF;
-        g.ind[2 * j + w] = 0;
-        g.iter[2 * j + w] = 0;
-        g.slot[2 * j + w] = -1;
-    }
-    if (ph == PH_NIL) store_cand(g.cand, pair, cand_nil());
-}
-
-// Advance every candidate: consume last round's results, emit this round's requests.
-__global__ void __launch_bounds__(256) sz_advance(SzArgs g) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= g.n_cand) return;
-    const DevFleet& f = g.f;
-    int ph = g.phase[j];
-    if (ph >= PH_DONE) return;
-    const int pair = g.cand_pair[j], s = pair / f.A, a = pair % f.A;
-    const float rmax = g.rmax[j];
-    if (ph == PH_SEARCH) {
-        bool all_done = true, nil = false, bail = false;
-        for (int w = 0; w < 2; ++w) {
-            const int k = 2 * j + w;
-            int st = g.sst[k];
-            if (st == SZ_DONE || st == SZ_OFF) continue;
-            const float target = w == 0 ? f.srv_slo_ttft[s] : f.srv_slo_itl[s];
-            float xmin = g.xmin[k], xmax = g.xmax[k];
-            float y = 0.0f;
-            if (st != SZ_START) {
-                const int slot = g.slot[k];
-                if (g.req_bail[slot]) { bail = true; break; }
-                y = g.req_out[slot].x;
-            }
-            float next = 0.0f;
-            bool emit = false;
-            if (st == SZ_START) {  // utils.go:29-31, 36-37
-                if (xmin > xmax) { nil = true; break; }
-                next = xmin; emit = true; st = SZ_WAIT_Y0;
-            } else if (st == SZ_WAIT_Y0) {
-                g.y0[k] = y;
-                if (within_tolerance(y, target, 1e-6f)) { g.xs[k] = xmin; st = SZ_DONE; }
-                else { next = xmax; emit = true; st = SZ_WAIT_Y1; }
-            } else if (st == SZ_WAIT_Y1) {
-                const float y0 = g.y0[k], y1 = y;
-                if (within_tolerance(y1, target, 1e-6f)) { g.xs[k] = xmax; st = SZ_DONE; }
-                else {
-                    const bool inc = y0 < y1;  // utils.go:45-51
-                    g.inc[k] = inc;
-                    if ((inc && target < y0) || (!inc && target > y0)) { g.xs[k] = xmin; g.ind[k] = -1; st = SZ_DONE; }
-                    else if ((inc && target > y1) || (!inc && target < y1)) { g.xs[k] = xmax; g.ind[k] = 1; st = SZ_DONE; }
-                    else {
-                        next = __fmul_rn(0.5f, __fadd_rn(xmin, xmax));
-                        g.xs[k] = next; g.iter[k] = 0; emit = true; st = SZ_WAIT_ITER;
-                    }
-                }
-            } else {  // SZ_WAIT_ITER: utils.go:54-68
-                const float xs = g.xs[k];
-                const bool inc = g.inc[k] != 0;
-                int it = g.iter[k];
-                if (within_tolerance(y, target, 1e-6f)) { st = SZ_DONE; }
-                else {
-                    const float pmin = xmin, pmax = xmax;
-                    if ((inc && target < y) || (!inc && target > y)) xmax = xs; else xmin = xs;
-                    g.xmin[k] = xmin; g.xmax[k] = xmax;
-                    ++it;
-                    // fixed point of the float32 interval: the remaining iterations repeat this solve
-                    if ((xmin == pmin && xmax == pmax) || it >= 100) { st = SZ_DONE; }
-                    else {
-                        next = __fmul_rn(0.5f, __fadd_rn(xmin, xmax));
-                        g.xs[k] = next; g.iter[k] = (uint8_t)it; emit = true;
-                    }
-                }
-            }
-            g.sst[k] = (uint8_t)st;
-            if (st == SZ_DONE && g.ind[k] < 0) { nil = true; break; }  // "target is below the bounded region"
-            if (emit) { sz_emit(g, j, w, next, k); all_done = false; }
-        }
-        if (bail) ph = PH_BAIL;
-        else if (nil) ph = PH_NIL;
-        else if (all_done) {
-            // queueanalyzer.go:231-241: lambda = min(lambdaStarTTFT, lambdaStarITL, lambdaStarTPS)
-            const float lmax = __fdiv_rn(rmax, 1000.0f);
-            float l_tps = lmax;
-            if (f.srv_slo_tps[s] > 0.0f) l_tps = __fmul_rn(lmax, __fsub_rn(1.0f, 0.1f));
-            const float lambda = go_minf(go_minf(g.xs[2 * j], g.xs[2 * j + 1]), l_tps);
-            const float rate = __fmul_rn(lambda, 1000.0f);
-            if (rate <= 0.0f || rate > rmax) ph = PH_NIL;  // Analyze: :135-143
-            else { sz_emit(g, j, 2, __fdiv_rn(rate, 1000.0f), 2 * j); ph = PH_WAIT_STAR; }
-        }
-    } else if (ph == PH_WAIT_STAR) {
-        const int slot = g.slot[2 * j];
-        if (g.req_bail[slot]) ph = PH_BAIL;
-        else {
-            const float rate_star = g.req_out[slot].x;  // metrics.Throughput
-            const float total_rate = total_rate_of(f, s);  // allocation.go:134-141
-            long long nrep = go_f64_to_int(ceil(__ddiv_rn((double)total_rate, (double)rate_star)));
-            const long long min_rep = f.srv_min_replicas[s];
-            if (nrep < min_rep) nrep = min_rep;
-            const long long total = (long long)num_instances(f, f.srv_model[s], a) * nrep;
-            g.rate_star[j] = rate_star;
-            g.nrep[j] = nrep;
-            g.cost[j] = __fmul_rn(f.acc_cost[a], (float)total);
-            const float rate = __fdiv_rn(total_rate, (float)nrep);  // :148-153
-            if (rate <= 0.0f || rate > rmax) ph = PH_NIL;
-            else { sz_emit(g, j, 3, __fdiv_rn(rate, 1000.0f), 2 * j); ph = PH_WAIT_FINAL; }
-        }
-    } else {  // PH_WAIT_FINAL
-        const int slot = g.slot[2 * j];
-        if (g.req_bail[slot]) ph = PH_BAIL;
-        else {
-            const float4 m = g.req_out[slot];
-            Cand c = cand_nil();
-            c.feasible = 1;
-            c.acc = a;
-            c.replicas = (int)g.nrep[j];
-            c.batch = g.cand_N[j];
-            c.cost = g.cost[j];
-            c.value = c.cost;
-            c.itl = m.z;
-            c.ttft = m.y;
-            c.rho = m.w;
-            c.max_rate = __fdiv_rn(g.rate_star[j], 1000.0f);
-            store_cand(g.cand, pair, c);
-            ph = PH_DONE;
-        }
-    }
-    if (ph == PH_NIL) store_cand(g.cand, pair, cand_nil());
-    if (ph == PH_BAIL) {
-        const int k = atomicAdd(g.fb_count, 1);
-        if (k < g.fb_cap) g.fb_list[k] = j;
-        store_cand(g.cand, pair, cand_nil());
-    }
-    g.phase[j] = (uint8_t)ph;
-}
-
-// Local counting sort of this round's requests by length class (keys precomputed by sz_emit).
-__global__ void __launch_bounds__(kSortThreads) sz_sort_local(SzArgs g) {
-    __shared__ uint8_t keys[kSortChunk];
-    __shared__ uint8_t sorted_keys[kSortChunk];
-    __shared__ unsigned hist[kClasses];
-    __shared__ unsigned cursor[kClasses];
-    __shared__ unsigned item_base;
-    const unsigned n_req = *g.n_req;
-    const unsigned base = blockIdx.x * kSortChunk;
-    if (base >= n_req) return;
-    if (threadIdx.x < kClasses) hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int n_here = (int)min((unsigned)kSortChunk, n_req - base);
-    for (int k = threadIdx.x; k < n_here; k += kSortThreads) {
-        const int key = g.req_key[base + k];
-        keys[k] = (uint8_t)key;
-        agg_inc(hist, key);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned run = 0;
-        for (int c0 = 0; c0 < kClasses; c0 += 32) {
-            const unsigned v = hist[c0 + threadIdx.x];
-            unsigned inc = v;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
-                if ((int)threadIdx.x >= d) inc += o;
-            }
-            cursor[c0 + threadIdx.x] = run + inc - v;
-            run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < n_here; k += kSortThreads) {
-        const int key = keys[k];
-        const unsigned pos = agg_inc(cursor, key);
-        g.ws.order[base + pos] = base + k;
-        sorted_keys[pos] = (uint8_t)key;
-    }
-    const int n_items = (n_here + 31) >> 5;
-    if (threadIdx.x == 0) item_base = atomicAdd(g.ws.item_count, (unsigned)n_items);
-    __syncthreads();
-    for (int w = threadIdx.x; w < n_items; w += kSortThreads) {
-        const unsigned cnt = (unsigned)min(32, n_here - 32 * w);
-        const int cls = sorted_keys[32 * w];
-        g.ws.items[item_base + w] = (unsigned long long)(base + 32 * w) | ((unsigned long long)cnt << 32) |
-                                    ((unsigned long long)cls << 40);
-        agg_inc(g.ws.item_count + 1, cls);
-    }
-}
 __global__ void __launch_bounds__(256) ws_items_scan(SortWs ws) {
     __shared__ unsigned tot[kClasses];
     tot[threadIdx.x] = ws.item_count[1 + threadIdx.x];
@@ -1653,36 +1386,6 @@ __global__ void __launch_bounds__(256) ws_items_scatter(SortWs ws) {
     ws.items_sorted[agg_inc(ws.item_count + 1 + kClasses, (int)((it >> 40) & 0xff))] = it;
 }
 
-// One request per lane, 32 requests of similar chain length per warp.
-__global__ void __launch_bounds__(256) sz_solve(SzArgs g) {
-    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned w = idx >> 5, lane = idx & 31;
-    if (w >= *g.ws.item_count) return;
-    const unsigned long long item = g.ws.items_sorted[w];
-    if (lane >= (unsigned)((item >> 32) & 0xff)) return;
-    const unsigned slot = g.ws.order[(unsigned)item + lane];
-    const unsigned id = g.req_id[slot];
-    const int j = (int)(id >> 2), kind = (int)(id & 3);
-    const DevFleet& f = g.f;
-    const int pair = g.cand_pair[j];
-    const int N = g.cand_N[j], K = N + N * f.ratio;
-    const float lambda = g.req_lam[slot];
-    ModelStats st;
-    const int rc = solve_private(g.tab + 4 * g.tab_off[j], N, K, lambda, st);
-    g.req_bail[slot] = rc != kSolveOk;
-    if (rc != kSolveOk) return;
-    const QParams q = qparams_of(f, pair / f.A, pair % f.A);
-    float4 out;
-    if (kind <= 1) {  // EvalTTFT / EvalITL: queueanalyzer.go:270-290
-        const float eff = effective_concurrency(q, st.avg_serv_time, N);
-        out.x = kind == 0 ? __fadd_rn(st.avg_wait_time, prefill_time(q, eff)) : decode_time(q, eff);
-        out.y = out.z = out.w = 0.0f;
-    } else {  // Analyze: :152-172
-        const Metrics m = metrics_from(q, N, st);
-        out = make_float4(m.throughput, m.ttft, m.avg_token_time, m.rho);
-    }
-    g.req_out[slot] = out;
-}
 
 // nil and zero-load candidates (everything the size kernel does not own).
 __global__ void trivial_kernel(DevFleet f, AllocCols cand) {

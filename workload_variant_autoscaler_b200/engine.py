@@ -24,6 +24,22 @@ class WvaError(RuntimeError):
         self.code = code
 
 
+def greedy_solve(fleet: Fleet, candidates: Allocs):
+    """``Solver.SolveGreedy`` + best-effort policies (pkg/solver/greedy.go:35-341) over a candidate table the
+    caller already holds (``wva_solve_greedy``: host only, no GPU).  ``candidates`` [S * A] carries
+    ``value`` = transition penalty (what ``Engine.analyze`` returns); it is modified in place where the reference
+    scales best-effort allocations.  Returns (candidates, winners [S])."""
+    L = _lib.lib()
+    if candidates.n != fleet.n_servers * fleet.n_acc:
+        raise ValueError("candidates must hold n_servers * n_acc records")
+    win = Allocs(fleet.n_servers)
+    fc, cc, wc = fleet.as_c(), candidates.as_c(), win.as_c()
+    rc = L.wva_solve_greedy(C.byref(fc), C.byref(cc), C.byref(wc))
+    if rc != 0:
+        raise WvaError(rc, L.wva_strerror(rc).decode())
+    return candidates, win
+
+
 class Engine:
     """One engine per GPU (one process per GPU in multi-GPU runs)."""
 

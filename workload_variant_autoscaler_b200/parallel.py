@@ -55,6 +55,38 @@ def solve_sharded(solve_local, fleet: Fleet, *, rank: int, world: int, all_gathe
     return unpack_winners(np.asarray(gathered), fleet.n_servers, world)
 
 
+def pack_candidates(cand: Allocs, pad_to: int) -> np.ndarray:
+    """Candidate table Allocs [n] -> int32 [10, pad_to] (float columns bit-cast), padding = nil candidates."""
+    return pack_winners(cand, pad_to)
+
+
+def solve_sharded_limited(analyze_local, fleet: Fleet, *, rank: int, world: int, all_gather, greedy=None):
+    """Limited (greedy) mode across ``world`` ranks: candidate generation — the expensive part —
+    shards over servers exactly like the unlimited solve; the greedy pass is ONE sequential walk over a shared
+    capacity map (pkg/solver/greedy.go:107-166) and does not shard, so the per-shard candidate tables are
+    all-gathered (one collective, S x A x 40 B) and every rank runs the same deterministic ``SolveGreedy`` over the
+    full table: every rank ends with the identical solution and no second collective is needed.
+
+    analyze_local(shard: Fleet) -> Allocs [S_shard * A] (``Server.Calculate``: the engine's ``analyze`` on this
+    rank's GPU); greedy(fleet, candidates) -> (candidates, winners), default = the library's ``wva_solve_greedy``.
+    Returns (candidates [S * A] after best-effort scaling, winners [S]) in the original server order.
+    """
+    from .engine import greedy_solve
+    A = fleet.n_acc
+    shard = fleet.shard(rank, world)
+    cand_local = analyze_local(shard)
+    pad = (fleet.n_servers + world - 1) // world
+    gathered = np.asarray(all_gather(pack_candidates(cand_local, pad * A)))  # [world, 10, pad * A]
+    full = Allocs(fleet.n_servers * A)
+    for r in range(world):
+        idx = shard_indices(fleet.n_servers, r, world)
+        for k, (name, dt) in enumerate(ALLOC_COLUMNS):
+            col = gathered[r, k, : idx.size * A].reshape(idx.size, A)
+            dst = getattr(full, name).reshape(fleet.n_servers, A)
+            dst[idx] = col.astype(np.uint8) if dt is np.uint8 else col.view(dt)
+    return (greedy or greedy_solve)(fleet, full)
+
+
 def torch_all_gather(group=None, device=None):
     """all_gather callable over torch.distributed (nccl on GPUs, gloo on CPU)."""
     import torch
