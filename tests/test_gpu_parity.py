@@ -384,3 +384,27 @@ def test_grid_wide_replica_axis_and_long_tables(engine, oracle_mod):
     fleet.srv_arrival_rpm[:] = np.float32([900.0, 2500.0])
     _grid_check(engine, oracle_mod, fleet, Grid([3, 1700], np.arange(1, 101)))
     _grid_check(engine, oracle_mod, fleet, Grid([64, 7, 64], np.arange(100, 0, -1)))
+
+
+@pytest.mark.parametrize("depth", ["1", "2", "3", "4", "5"])
+def test_size_rounds_every_tree_depth(engine, oracle_mod, monkeypatch, depth):
+    """The round-based size path resolves D reference iterations per round from a tree of 2^D - 1 speculative
+    midpoints (wva_size.cuh); the results must not depend on D.  The small-fleet kernel is switched off here."""
+    monkeypatch.setenv("WVA_SIZE_SMALL_MAX", "0")
+    monkeypatch.setenv("WVA_SIZE_DEPTH", depth)
+    fleet = synth_fleet(40, 4, seed=101 + int(depth), max_batch_choices=(1, 2, 4, 8, 16, 32, 64, 128), zero_load_frac=0.1)
+    fleet.srv_min_replicas[::6] = 0
+    cand_o, win_o = oracle_mod.solve(fleet)
+    cand_g, win_g = engine.solve(fleet)
+    assert_allocs_equal(cand_g, cand_o, f"size candidates (D = {depth})")
+    assert_allocs_equal(win_g, win_o, f"winners (D = {depth})")
+
+
+def test_size_small_fleet_kernel_on_a_larger_fleet(engine, oracle_mod, monkeypatch):
+    """The warp-per-candidate kernel (small fleets) forced onto 1,200 candidates with batch sizes up to 256."""
+    monkeypatch.setenv("WVA_SIZE_SMALL_MAX", "100000")
+    fleet = synth_fleet(300, 4, seed=107, max_batch_choices=(4, 8, 16, 32, 64, 128, 256))
+    cand_o, win_o = oracle_mod.solve(fleet)
+    cand_g, win_g = engine.solve(fleet)
+    assert_allocs_equal(cand_g, cand_o, "size candidates (warp per candidate)")
+    assert_allocs_equal(win_g, win_o, "winners (warp per candidate)")

@@ -587,7 +587,13 @@ int enqueue_size(wva_handle* h, const AllocCols& cand, const AllocCols* winners)
     g.fb_list = (int*)h->d_fb_list.p;
     g.fb_cap = std::max(n, 1);
     CK(cudaEventRecord(h->ev_k0, h->stream));
-    if (n > 0) {
+    int small_max = 1024;  // up to here a warp per candidate beats rounds (the GPU is mostly empty either way)
+    if (const char* e = getenv("WVA_SIZE_SMALL_MAX")) small_max = atoi(e);
+    if (n > 0 && n <= small_max) {
+        size_warp_kernel<<<(unsigned)((n + 3) / 4), 128, 0, h->stream>>>(g, (const double*)h->d_sz_tab.p,
+                                                                          (const long long*)h->d_sz_off.p);
+        h->launches++;
+    } else if (n > 0) {
         rc = run_size_rounds(h, g, n);
         if (rc) return rc;
     }

@@ -387,6 +387,138 @@ __global__ void __launch_bounds__(256) sz2_solve(Sz2Args g) {
     g.req_out[slot] = out;
 }
 
+// ---------------------------------------------------------------------------
+// Small fleets (BASELINE configs[0]: one VariantAutoscaling = one candidate): ONE warp per candidate runs the whole
+// CreateAllocation in one launch — the same speculative midpoint trees, but evaluated by the warp's lanes (round one:
+// the two end points + 15 midpoints = 4 iterations; later rounds: 31 midpoints = 5 iterations) and walked in
+// registers with warp shuffles.  No rounds, no sort, no host round trip: a reconcile of a handful of variants is
+// three launches (trivial, this, unlimited argmin) instead of sixty.  Same lambdas, same solves, same comparisons
+// as the round-based path and the reference.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float sz_eval(const QParams& q, int which, const double* tab, int N, int K, float x, int& bail) {
+    ModelStats st;
+    if (solve_shared(tab, N, K, x, st) != kSolveOk) { bail = 1; return 0.0f; }
+    const float eff = effective_concurrency(q, st.avg_serv_time, N);  // queueanalyzer.go:270-290
+    return which == 0 ? __fadd_rn(st.avg_wait_time, prefill_time(q, eff)) : decode_time(q, eff);
+}
+__global__ void __launch_bounds__(128) size_warp_kernel(SizeArgs g, const double* __restrict__ tabs,
+                                                        const long long* __restrict__ tab_off) {
+    const int j = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= g.n_cand) return;
+    const DevFleet& f = g.f;
+    const int pair = g.cand_pair[j], s = pair / f.A, a = pair % f.A;
+    const int N = g.cand_N[j], K = N + N * f.ratio;
+    const double* tab = tabs + 4 * tab_off[j];
+    const QParams q = qparams_of(f, s, a);
+    const float rmin = rate_min_of((float)tab[0]), rmax = rate_max_of((float)tab[4 * (N - 1)]);
+    const float slo_ttft = f.srv_slo_ttft[s], slo_itl = f.srv_slo_itl[s], slo_tps = f.srv_slo_tps[s];
+    bool nil = K < 2 || slo_itl < 0.0f || slo_ttft < 0.0f || slo_tps < 0.0f;  // queuemodel.go:31, TargetPerf.check
+    bool bail = false;
+    const float lmin = __fdiv_rn(rmin, 1000.0f), lmax = __fdiv_rn(rmax, 1000.0f);
+    float xstar[2] = {lmax, lmax};  // lambdaStar when a target is disabled (queueanalyzer.go:205,218)
+    for (int w = 0; w < 2 && !nil && !bail; ++w) {
+        const float target = w == 0 ? slo_ttft : slo_itl;
+        if (!(target > 0.0f)) continue;
+        float lo = lmin, hi = lmax;
+        if (lo > hi) { nil = true; break; }  // utils.go:29-31
+        bool first = true, searching = true, inc = false;
+        int it = 0, ind = 0;
+        float xs = 0.0f;
+        while (searching && !bail) {
+            // this lane's evaluation point: round one = {xmin, xmax, nodes 1..15}, later rounds = nodes 1..31
+            const int D = first ? 4 : 5;
+            const int v_mine = first ? lane - 1 : lane + 1;
+            const bool has = first ? lane < 17 : lane < 31;
+            float x = lo;
+            if (first && lane == 1) x = hi;
+            if (has && !(first && lane < 2)) x = sz_node_value(v_mine, lo, hi);
+            float y = 0.0f;
+            int b = 0;
+            if (has) y = sz_eval(q, w, tab, N, K, x, b);
+            __syncwarp();
+            if (first) {  // utils.go:36-51: the two boundary evaluations
+                const float y0 = __shfl_sync(0xffffffffu, y, 0), y1 = __shfl_sync(0xffffffffu, y, 1);
+                const int b0 = __shfl_sync(0xffffffffu, b, 0), b1 = __shfl_sync(0xffffffffu, b, 1);
+                if (b0) { bail = true; break; }
+                if (within_tolerance(y0, target, 1e-6f)) { xs = lo; searching = false; }
+                else {
+                    if (b1) { bail = true; break; }
+                    if (within_tolerance(y1, target, 1e-6f)) { xs = hi; searching = false; }
+                    else {
+                        inc = y0 < y1;
+                        if ((inc && target < y0) || (!inc && target > y0)) { xs = lo; ind = -1; searching = false; }
+                        else if ((inc && target > y1) || (!inc && target < y1)) { xs = hi; ind = 1; searching = false; }
+                    }
+                }
+            }
+            if (searching) {  // utils.go:54-68, D iterations over the evaluated tree
+                int v = 1;
+                for (int level = 0; level < D; ++level) {
+                    const int src = first ? v + 1 : v - 1;  // the lane that evaluated node v
+                    const float yv = __shfl_sync(0xffffffffu, y, src);
+                    const int bv = __shfl_sync(0xffffffffu, b, src);
+                    xs = sz_mid(lo, hi);
+                    if (bv) { bail = true; break; }
+                    if (within_tolerance(yv, target, 1e-6f)) { searching = false; break; }
+                    const float pmin = lo, pmax = hi;
+                    if ((inc && target < yv) || (!inc && target > yv)) { hi = xs; v = 2 * v; }
+                    else { lo = xs; v = 2 * v + 1; }
+                    ++it;
+                    if ((lo == pmin && hi == pmax) || it >= 100) { searching = false; break; }
+                }
+            }
+            first = false;
+        }
+        xstar[w] = xs;
+        if (ind < 0) nil = true;  // "target is below the bounded region"
+    }
+    Cand out = cand_nil();
+    if (!nil && !bail) {
+        // queueanalyzer.go:231-241, allocation.go:134-163 — every lane computes the same values
+        float l_tps = lmax;
+        if (slo_tps > 0.0f) l_tps = __fmul_rn(lmax, __fsub_rn(1.0f, 0.1f));
+        const float lambda = go_minf(go_minf(xstar[0], xstar[1]), l_tps);
+        const float rate0 = __fmul_rn(lambda, 1000.0f);
+        ModelStats st;
+        if (rate0 <= 0.0f || rate0 > rmax) nil = true;
+        else if (solve_shared(tab, N, K, __fdiv_rn(rate0, 1000.0f), st) != kSolveOk) bail = true;
+        else {
+            const float rate_star = metrics_from(q, N, st).throughput;
+            const float total_rate = total_rate_of(f, s);
+            long long nrep = go_f64_to_int(ceil(__ddiv_rn((double)total_rate, (double)rate_star)));
+            const long long min_rep = f.srv_min_replicas[s];
+            if (nrep < min_rep) nrep = min_rep;
+            const long long total = (long long)num_instances(f, f.srv_model[s], a) * nrep;
+            const float cost = __fmul_rn(f.acc_cost[a], (float)total);
+            const float rate = __fdiv_rn(total_rate, (float)nrep);
+            if (rate <= 0.0f || rate > rmax) nil = true;
+            else if (solve_shared(tab, N, K, __fdiv_rn(rate, 1000.0f), st) != kSolveOk) bail = true;
+            else {
+                const Metrics m = metrics_from(q, N, st);
+                out.feasible = 1;
+                out.acc = a;
+                out.replicas = (int)nrep;
+                out.batch = N;
+                out.cost = cost;
+                out.value = cost;
+                out.itl = m.avg_token_time;
+                out.ttft = m.ttft;
+                out.rho = m.rho;
+                out.max_rate = __fdiv_rn(rate_star, 1000.0f);
+            }
+        }
+    }
+    if (lane == 0) {
+        if (bail) {
+            const int k = atomicAdd(g.fb_count, 1);
+            if (k < g.fb_cap) g.fb_list[k] = j;
+            out = cand_nil();
+        }
+        store_cand(g.cand, pair, out);
+    }
+}
+
 // Per-round reset of the device counters (one tiny kernel instead of two memsets; part of the captured round).
 __global__ void sz2_round_reset(Sz2Args g) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
