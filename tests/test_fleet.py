@@ -98,3 +98,25 @@ def test_as_c_cache_follows_the_arrays():
     c3 = f.as_c()
     assert C.cast(c3.srv_arrival_rpm, C.c_void_p).value == f.srv_arrival_rpm.ctypes.data
     assert c3.srv_arrival_rpm[0] == 3.0 and c3.n_servers == 4
+
+
+def test_packer_fixture_repeated_names_last_wins():
+    """tests/golden/packer_fixture.json is the fixture the two packers share (Fleet.from_spec here, pack() in
+    go/wvab200/wvab200.go): repeated accelerator / server names follow System.SetFromSpec (pkg/core/system.go:99-101,
+    151-153: the map entry is replaced), i.e. the last spec wins at the position of the first."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "packer_fixture.json")))
+    f = Fleet.from_spec(fx["spec"])
+    # hand-derived from the spec
+    assert f.acc_names == ["A100", "H100"] and f.server_names == ["a:ns", "b:ns"]
+    assert list(f.acc_cost) == [np.float32(41.5), np.float32(65.0)] and list(f.acc_multiplicity) == [4, 2]
+    assert f.type_names == ["GPU_A100_80", "GPU_H100", "TPU"] and list(f.type_capacity) == [0, 7, 3]
+    assert list(f.srv_min_replicas) == [2, 0] and list(f.srv_max_batch) == [4, 0]
+    assert list(f.srv_cur_acc) == [1, ACC_NONE] and list(f.srv_cur_replicas) == [3, 0]
+    assert list(f.srv_arrival_rpm) == [np.float32(600.0), np.float32(0.0)]
+    # and the whole SoA as frozen in the fixture (what the Go packer must reproduce)
+    for name, want in fx["soa"].items():
+        got = getattr(f, name)
+        got = got.reshape(-1).tolist() if isinstance(got, np.ndarray) else got
+        assert got == want, name
