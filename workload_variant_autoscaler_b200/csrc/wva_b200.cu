@@ -867,7 +867,7 @@ int enqueue_grid(wva_handle* h, GridPlan& plan, const AllocCols& winners) {
         // one warp per item; the item count lives on the device, so launch for the worst case
         const size_t max_items = (plan.n_cells + 31) / 32 + (size_t)plan.n_blocks;
         (void)max_items;
-        grid_items_scatter<<<(unsigned)(4 * h->sm_count), 256, 0, h->stream>>>(g);  // warp per item, persistent
+        grid_items_scatter<<<(unsigned)(16 * h->sm_count), 256, 0, h->stream>>>(g);  // warp per item (grid-stride)
         h->launches++;
         CK(cudaEventRecord(h->ev_k0, h->stream));  // wva_last_kernel_ms = the dominant kernel alone
         const size_t smem = (size_t)kGkWarps * kGkWarpD * sizeof(double);

@@ -210,8 +210,13 @@ __device__ long long wva_prof[16];
 // trip to L2 for everything it reads; pass 2 re-uses that window when the whole head fits in it (hmax <= 64).
 // Later windows are 32 entries, prefetched in registers as before.  `tbuf` holds kStagedSlots entries.
 // REV: pairs of checked steps a lane set takes on the per-step path before it returns to the block vote (0 = never returns)
+__device__ __forceinline__ void dev_cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 constexpr int kStagedFirst = 64;   // entries in the first staged window
-constexpr int kStagedSlots = 96;   // slots of tbuf: pass 2 may index up to (hmax - 1) + 31 <= 94 when it re-uses the window
+constexpr int kStagedSlots = 96;   // window slots of tbuf: pass 2 may index up to (hmax - 1) + 31 <= 94 when it re-uses the window
+constexpr int kStagedTbufD = kStagedSlots * 4 + 96;  // doubles per warp: the window, then the lanes' tail entries [3][32]
 template <int STASH, int PF = 10, bool STAGED = false, int REV = 1>
 __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st,
                                            double* __restrict__ stash, double* __restrict__ tbuf = nullptr) {
@@ -224,23 +229,49 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     // entry 0.
     bool staged = false;
     int hmax = 0, hmin = 0;
-    double4 win0, win1;
-    Recip T;  // tail entry servRate[N-1]
+    // The tail entry servRate[N-1] is needed wherever a loop hands over to the next one.  Holding it in registers
+    // for the whole solve cost the pure-tail loops six registers and ptxas a worse schedule (54.7 instead of 42.5
+    // cycles per state, measured); re-loading it from the table at every hand-over was one of the dependent trips
+    // to L2 this version removes.  So a staged solve parks it in shared memory (tsave[3][32], one column per lane)
+    // and WVA_LOAD_TAIL brings it back with three LDS; a solve that is not staged reads the table as before.
+    double* const tsave = STAGED ? tbuf + kStagedSlots * 4 + (threadIdx.x & 31) : nullptr;
+#define WVA_LOAD_TAIL(R)                                                    \
+    if (STAGED && staged) {                                                 \
+        (R).b = tsave[0];                                                   \
+        (R).yh = tsave[32];                                                 \
+        (R).yl = tsave[64];                                                 \
+    } else {                                                                \
+        load_recip(tab, nh, R);                                             \
+    }
     if (STAGED) {
         staged = warp_mask == 0xffffffffu && __all_sync(0xffffffffu, tab == (const double*)__shfl_sync(0xffffffffu, (unsigned long long)tab, 0));
         if (staged) {
             hmax = __reduce_max_sync(0xffffffffu, nh);
             hmin = __reduce_min_sync(0xffffffffu, nh);
+            // the first window goes straight from the table into shared memory (cp.async: holding its 64 bytes per
+            // lane in registers across the prologue made ptxas allocate the pure-tail loops worse: 54.7 instead
+            // of 42.5 cycles per state, measured)
             const double4* tab4 = reinterpret_cast<const double4*>(tab);
             const int lane = threadIdx.x & 31;
-            win0 = tab4[min(1 + lane, hmax)];
-            win1 = tab4[min(33 + lane, hmax)];
+            double4* tb0 = reinterpret_cast<double4*>(tbuf);
+            const double4* s0 = tab4 + min(1 + lane, hmax);
+            const double4* s1 = tab4 + min(33 + lane, hmax);
+            dev_cp_async16(tb0 + lane, s0);
+            dev_cp_async16(reinterpret_cast<char*>(tb0 + lane) + 16, reinterpret_cast<const char*>(s0) + 16);
+            dev_cp_async16(tb0 + 32 + lane, s1);
+            dev_cp_async16(reinterpret_cast<char*>(tb0 + 32 + lane) + 16, reinterpret_cast<const char*>(s1) + 16);
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
     }
     load_recip(tab, 0, A);
-    load_recip(tab, nh, T);
-    const double tail_b = T.b;
+    load_recip(tab, nh, B);
+    const double tail_b = B.b;
     st.tail_rate = (float)tail_b;
+    if (STAGED && staged) {
+        tsave[0] = B.b;
+        tsave[32] = B.yh;
+        tsave[64] = B.yl;
+    }
     bool bail = !in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail_b, kHiRateLo, kHiRateHi) ||
                 !in_window(A.b, kHiRateLo, kHiRateHi);
     const bool tail_mono = rate_below(lambda, (float)tail_b);
@@ -301,6 +332,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             double4* tb = reinterpret_cast<double4*>(tbuf);
             const int lane = threadIdx.x & 31;
             bool ok = true;
+            Recip T;
+            WVA_LOAD_TAIL(T)
 #define WVA_SP1_GROUP(SEL, ST)                                                                                    \
     _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                               \
         const double4 e = tb[k + u];                                                                              \
@@ -327,9 +360,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         if (n + 4 <= hmin) { WVA_SP1_GROUP(false, ST) } else { WVA_SP1_GROUP(true, ST) }                          \
     }
             // first window: entries 1..64 in slots 0..63 (slot k holds the entry of step 1 + k)
-            __syncwarp();
-            tb[lane] = win0;
-            tb[32 + lane] = win1;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
             double4 nxt;  // later windows travel in registers
             if (kStagedFirst + 1 < hmax) nxt = tab4[min(kStagedFirst + 1 + lane, hmax)];
@@ -351,8 +382,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
 #endif
         // invariant at the top of the loop: A = triple of step n, B = triple of step n+1 (the tail entry is
         // already in registers: a warp that is past its heads issues no load here)
-        A = T;
-        B = T;
+        WVA_LOAD_TAIL(A)
+        B = A;
         if (n < nh) load_recip(tab, n, A);
         if (n + 1 < nh) load_recip(tab, n + 1, B);
         while (n < n_stop) {
@@ -412,14 +443,14 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             if (p == 0.0) { j_end = n + 1; break; }
             if (!(p > 0.0) || hp >= kHiPHi) { bail = true; break; }
             // rare: one step outside the fast loop (exact IEEE division when p is tiny)
-            A = T;
+            WVA_LOAD_TAIL(A)
             if (n < nh) load_recip(tab, n, A);
             p = hp >= kHiPLo ? div_recip(__dmul_rn(p, lam), A) : __ddiv_rn(__dmul_rn(p, lam), A.b);
             sum = __dadd_rn(sum, p);
             if (STASH > 0 && n < STASH) stash[n * 32] = p;
             ++n;
-            A = T;
-            B = T;
+            WVA_LOAD_TAIL(A)
+            B = A;
             if (n < nh) load_recip(tab, n, A);
             if (n + 1 < nh) load_recip(tab, n + 1, B);
         }
@@ -491,7 +522,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 // left early: p = p[i] is outside the fast window (tiny or zero): generic loop handles it
             } else if (i < j_end) {
                 // continue the recurrence from the last stashed state: p[i] = step(p[i-1])
-                A = T;
+                WVA_LOAD_TAIL(A)
                 if (i - 1 < nh) load_recip(tab, i - 1, A);
                 const double pprev = stash[(i - 2) * 32];
                 p = WVA_FASTWIN(pprev, kHiPLo, kHiPHi - kHiPLo) ? div_recip(__dmul_rn(pprev, lam), A)
@@ -505,6 +536,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             double4* tb = reinterpret_cast<double4*>(tbuf);
             const int lane = threadIdx.x & 31;
             bool ok = true;
+            Recip T;
+            WVA_LOAD_TAIL(T)
             // when the whole head fits in the first window of pass 1 (entry e in slot e - 1) it is still there
             const bool reuse = hmax <= kStagedFirst;
             const double4* tbp = tb;
@@ -566,8 +599,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         wva_prof[8] = i;
 #endif
         // invariant at the top of the loop: A = triple of the step out of state i, B = of state i+1
-        A = T;
-        B = T;
+        WVA_LOAD_TAIL(A)
+        B = A;
         if (i < nh) load_recip(tab, i, A);
         if (i + 1 < nh) load_recip(tab, i + 1, B);
         while (i < j_end) {
@@ -621,7 +654,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             if (i >= j_end) break;
             if (p == 0.0) { pn = 0.0; break; }
             // rare: tiny p, exact IEEE divisions
-            A = T;
+            WVA_LOAD_TAIL(A)
             if (i < nh) load_recip(tab, i, A);
             pn = __ddiv_rn(p, sum);
             acc = __dadd_rn(acc, __dmul_rn(di, pn));
@@ -632,8 +665,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             }
             p = __ddiv_rn(__dmul_rn(p, lam), A.b);
             ++i;
-            A = T;
-            B = T;
+            WVA_LOAD_TAIL(A)
+            B = A;
             if (i < nh) load_recip(tab, i, A);
             if (i + 1 < nh) load_recip(tab, i + 1, B);
         }
@@ -652,6 +685,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     float w = __fsub_rn(st.avg_resp_time, st.avg_serv_time);
     if (w < 0.0f) w = 0.0f;
     st.avg_wait_time = w;
+#undef WVA_LOAD_TAIL
     return bail ? kSolveBail : kSolveOk;
 }
 

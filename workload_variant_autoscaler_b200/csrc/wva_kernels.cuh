@@ -339,7 +339,7 @@ struct GridArgs {
     CellCols cells;          // internal per-cell columns (ttft, itl, rho always present)
     float4* pair_rec;        // [S*A][3] per pair: {alpha, beta, gamma, delta}, {in_tok, out_tok (int bits), slo_ttft, slo_itl},
                              // {min_replicas, tps flag (int bits), 0, 0} -- one 48-byte record instead of ten scattered loads
-    uint4* recs;             // [items][32] per sorted cell: {cell, lambda bits, table entry offset, batch size | pad flag << 31}
+    uint4* recs;             // [items][32] per sorted cell: {cell, lambda bits, table entry offset, batch size | class << 23 | pad << 31}
     int want_cells;          // 0: the caller did not ask for the cell table -> cells that share their row's chain store
                              // nothing (grid_finalize recomputes the few winners among them); 1: every cell is stored
     int* fb_count;           // cells that need the stored-vector fallback
@@ -482,6 +482,50 @@ __device__ __forceinline__ Metrics shared_cell_metrics(const PairConst& pc, doub
     return m;
 }
 
+// The same evaluation when (float)avgNumInServers does not depend on the batch size.  avgNumInServers =
+// acc + (1 - sumP) * N in float64, and 1 - sumP is a few ulps of 1 at most (the chain died before state N), so
+// for all N <= Nmax the float64 value stays inside the float32 rounding interval of acc unless acc sits within
+// ~1e-13 relative of an interval edge.  row_invariant() proves it for a (pair, replica level) with an exact bound:
+// lo_b, hi_b = the float32 rounding boundaries around acc (exact in float64); |in_serv - acc| <= |m| N (1 + 2^-52)
+// + acc 2^-53, and both distances are exact differences (Sterbenz), so d > 2 RN(|m| Nmax) + acc 2^-50 implies
+// lo_b < in_serv < hi_b, i.e. (float)in_serv == (float)acc for every batch size of the grid.  Then the service
+// time, the waiting time and the unclamped effective concurrency are constants of the row and a cell costs a
+// min, two multiply-adds and the SLO comparisons.  Rows that fail the test take shared_cell_metrics.
+struct RowInv {
+    float f0, w0, effu;  // (float)avgNumInServers, waiting time, max(effective concurrency, 0) before the clamp at N
+};
+__device__ __forceinline__ bool row_invariant(const PairConst& pc, double acc, double one_m_sump, float resp, float lambda,
+                                              int Nmax, RowInv& ri) {
+    const float f0 = (float)acc;
+    if (!(f0 > 1e-30f && f0 < 1e30f)) return false;
+    const float up = __uint_as_float(__float_as_uint(f0) + 1u), dn = __uint_as_float(__float_as_uint(f0) - 1u);
+    const double hi_b = 0.5 * ((double)f0 + (double)up), lo_b = 0.5 * ((double)dn + (double)f0);
+    const double d = fmin(hi_b - acc, acc - lo_b);
+    const double tb = __dmul_rn(fabs(one_m_sump), (double)Nmax);
+    if (!(d > __dadd_rn(__dmul_rn(2.0, tb), __dmul_rn(acc, 0x1p-50)))) return false;
+    const float thr = __fmul_rn(lambda, __fsub_rn(1.0f, 0.0f));
+    const float serv = __fdiv_rn(f0, thr);
+    float w = __fsub_rn(resp, serv);
+    if (w < 0.0f) w = 0.0f;
+    ri.f0 = f0;
+    ri.w0 = w;
+    ri.effu = go_maxf(__fdiv_rn(__fsub_rn(serv, pc.ec_base), pc.ec_den), 0.0f);
+    return true;
+}
+__device__ __forceinline__ Metrics shared_cell_metrics_inv(const PairConst& pc, const RowInv& ri, float lambda, int N,
+                                                           bool want_rho) {
+    const float fN = (float)N;
+    const float eff = go_minf(ri.effu, fN);
+    Metrics m;
+    m.avg_prefill_time = pc.in_zero ? 0.0f : __fadd_rn(pc.gamma, __fmul_rn(pc.d_in, eff));
+    m.avg_token_time = __fadd_rn(pc.alpha, __fmul_rn(pc.beta, eff));
+    m.rho = want_rho ? go_minf(go_maxf(__fdiv_rn(ri.f0, fN), 0.0f), 1.0f) : 0.0f;
+    m.throughput = __fmul_rn(__fmul_rn(lambda, __fsub_rn(1.0f, 0.0f)), 1000.0f);
+    m.avg_wait_time = ri.w0;
+    m.ttft = __fadd_rn(ri.w0, m.avg_prefill_time);
+    return m;
+}
+
 // One CTA per (server, accelerator) pair, one lane per replica level: the chain every large-enough
 // batch size shares.  The pair's table is staged in shared memory first (coalesced), so the serial
 // chains read it at shared-memory latency instead of waiting for L2 on every step.
@@ -619,9 +663,13 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
         // lane's own row constants (its first two replica levels: rate, lambda, the row's shared chain)
         struct LaneRow {
             float4 rt;
-            double acc, one_m_sump;  // shared-chain results of the row: sum(i p[i]), 1 - sumP
-            float resp;              // avgNumInSystem / throughput (does not depend on the batch size)
+            // shared-chain results of the row.  inv == false: a = sum(i p[i]), b = 1 - sumP, r = resp (avgNumInSystem /
+            // throughput).  inv == true (row_invariant holds): the three floats of RowInv ride in the same registers
+            // (a = {f0, w0}, r = effu), so the hot loop carries no more state than before.
+            double a, b;
+            float r;
             int jl, rep;
+            bool inv;
         };
         LaneRow c0{}, c1{};
         unsigned sa = (row0 + warp) / B;
@@ -635,10 +683,17 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
             const size_t rowid = (size_t)sa * R + ri;
             c.rt = g.rt[(unsigned)s * R + ri];
             c.jl = g.row_j[rowid];
-            c.acc = g.row_acc[rowid];
-            c.one_m_sump = __dsub_rn(1.0, g.row_sump[rowid]);
-            c.resp = row_resp_time(c.acc, c.rt.y);
+            c.a = g.row_acc[rowid];
+            c.b = __dsub_rn(1.0, g.row_sump[rowid]);
+            c.r = row_resp_time(c.a, c.rt.y);
             c.rep = g.replicas[ri];
+            c.inv = false;
+            RowInv inv;
+            if (c.jl != INT_MAX && row_invariant(pc, c.a, c.b, c.r, c.rt.y, g.Bmax, inv)) {
+                c.inv = true;
+                c.a = __hiloint2double(__float_as_int(inv.w0), __float_as_int(inv.f0));
+                c.r = inv.effu;
+            }
         };
         for (unsigned row = row0 + warp; row <= row1; row += kSortThreads / 32, bi += kSortThreads / 32) {
             while (bi >= (int)B) {
@@ -674,7 +729,16 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
                     if (c.jl != INT_MAX && b >= c.jl + 2 && K < (1 << 23)) {
                         done_here = true;
                         // the whole solve is shared with the row: only the N-dependent tail is per cell
-                        const Metrics m = shared_cell_metrics(pc, c.acc, c.one_m_sump, c.resp, c.rt.y, b);
+                        Metrics m;
+                        if (c.inv) {
+                            RowInv inv;
+                            inv.f0 = __int_as_float(__double2loint(c.a));
+                            inv.w0 = __int_as_float(__double2hiint(c.a));
+                            inv.effu = c.r;
+                            m = shared_cell_metrics_inv(pc, inv, c.rt.y, b, g.want_cells != 0);
+                        } else {
+                            m = shared_cell_metrics(pc, c.a, c.b, c.r, c.rt.y, b);
+                        }
                         const bool feas = cell_feasible(fr, c.rep, c.rt.y, m);
                         if (g.want_cells) store_cell(g, cell, 1, feas ? 1 : 0, m);
                         if (feas) {
@@ -869,7 +933,9 @@ __global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
         const float lambda = g.rt[s * g.R + ri].y;
         const unsigned toff = (unsigned)g.pair_tab_off[s * f.A + a];
         const unsigned b = (unsigned)g.batch[bi];
-        g.recs[(size_t)pos * 32 + lane] = make_uint4(cell, __float_as_uint(lambda), toff, b | (valid ? 0u : 0x80000000u));
+        // w: batch size (bits 0..22) | the item's length class (bits 23..30) | pad flag (bit 31)
+        g.recs[(size_t)pos * 32 + lane] = make_uint4(cell, __float_as_uint(lambda), toff,
+                                                     b | ((unsigned)((it >> 40) & 0xff) << 23) | (valid ? 0u : 0x80000000u));
     }
 }
 
@@ -887,14 +953,12 @@ __global__ void __launch_bounds__(256) grid_items_scatter(GridArgs g) {
 // ---------------------------------------------------------------------------
 constexpr int kQLongN = 2 * kClasses + 1, kQLongCtr = kQLongN + 1, kQShortCtr = kQLongN + 2;  // in item_count[]
 
-// Per-warp shared memory of grid_kernel (doubles): the pass-1 stash, the staged table window, two record slots
-// (the current item's records and the next one's, copied by cp.async while the current item is being solved)
-// and the pair record of the current item.
+// Per-warp shared memory of grid_kernel (doubles): the pass-1 stash, the staged table window (+ the lanes' tail
+// entries) and the pair record of the current item.
 constexpr int kGkStashD = kGridStash * 32;              // [state][lane]
-constexpr int kGkTbufD = kStagedSlots * 4;              // staged table entries of 4 doubles
-constexpr int kGkRecD = 2 * 32 * 2;                     // 2 slots x 32 lanes x 16 bytes
+constexpr int kGkTbufD = kStagedTbufD;                  // staged table window + the lanes' tail entries
 constexpr int kGkPairD = 8;                             // 48-byte pair record (padded to 64)
-constexpr int kGkWarpD = kGkStashD + kGkTbufD + kGkRecD + kGkPairD;
+constexpr int kGkWarpD = kGkStashD + kGkTbufD + kGkPairD;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -912,7 +976,7 @@ __device__ __forceinline__ void item_run(const GridArgs& g, unsigned w, const ui
     const DevFleet& f = g.f;
     double* stash_warp = warp_smem;
     double* tbuf_warp = warp_smem + kGkStashD;
-    float4* pair_buf = reinterpret_cast<float4*>(warp_smem + kGkStashD + kGkTbufD + kGkRecD);
+    float4* pair_buf = reinterpret_cast<float4*>(warp_smem + kGkStashD + kGkTbufD);
     const unsigned idx = w * 32 + lane;
     const long long t_start = g.dbg_cycles ? clock64() : 0;
     unsigned long long t_start_ns = 0;
@@ -920,7 +984,7 @@ __device__ __forceinline__ void item_run(const GridArgs& g, unsigned w, const ui
     const unsigned cell = rec.x;
     const float lambda = __uint_as_float(rec.y);
     const double* tab = g.tab + 4 * (size_t)rec.z;
-    const int N = (int)(rec.w & 0x7fffffffu);
+    const int N = (int)(rec.w & 0x7fffffu);
     const bool valid = (rec.w >> 31) == 0;
     const int K = N + N * f.ratio;
     const unsigned pair = cell / ((unsigned)g.B * (unsigned)g.R);
@@ -975,10 +1039,9 @@ __device__ __forceinline__ void item_run(const GridArgs& g, unsigned w, const ui
 }
 
 __global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
-    extern __shared__ double grid_smem[];
+    extern __shared__ __align__(16) double grid_smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* warp_smem = grid_smem + (size_t)warp * kGkWarpD;
-    uint4* rec_slot = reinterpret_cast<uint4*>(warp_smem + kGkStashD + kGkTbufD);  // [2][32]
     const unsigned n_items = g.item_count[0], n_long = g.item_count[kQLongN];
     const bool sub0 = (warp & 3) == 0;
     // the long items are spread over as few CTAs as possible (long_per_sm per CTA): the other CTAs keep all
@@ -1005,30 +1068,17 @@ __global__ void __launch_bounds__(kGkThreads, 1) grid_kernel(GridArgs g) {
     } else if (sub0 && my_long > 0 && !long_warp && (int)(warp >> 2) >= my_long + g.long_share) {
         asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
     }
-    // short queue, software-pipelined two items deep: while item k is being solved, the records of item k + 1
-    // travel into the other record slot (cp.async: no registers) and the queue slot of item k + 2 is being
-    // fetched (one register in lane 0).  At the top of an iteration everything the solver needs is one
-    // shared-memory read away.
-    unsigned w_cur = 0, w_nxt = 0;
-    if (lane == 0) {
-        w_cur = atomicAdd(g.item_count + kQShortCtr, 2u);
-        w_nxt = w_cur + 1;
-    }
-    w_cur = __shfl_sync(0xffffffffu, w_cur, 0);
-    w_nxt = __shfl_sync(0xffffffffu, w_nxt, 0);
-    if (w_cur < n_items) cp_async16(rec_slot + lane, g.recs + (size_t)w_cur * 32 + lane);
-    cp_async_commit();
-    for (unsigned k = 0;; ++k) {
-        if (w_cur >= n_items) break;
-        if (w_nxt < n_items) cp_async16(rec_slot + 32 * ((k + 1) & 1) + lane, g.recs + (size_t)w_nxt * 32 + lane);
-        cp_async_commit();
-        unsigned w_nn = 0;
-        if (lane == 0) w_nn = atomicAdd(g.item_count + kQShortCtr, 1u);
-        cp_async_wait<1>();  // all but the newest group: this item's records have landed (each lane reads its own)
-        const uint4 rec = rec_slot[32 * (k & 1) + lane];
-        item_run(g, w_cur, rec, lane, warp_smem);
-        w_cur = w_nxt;
-        w_nxt = __shfl_sync(0xffffffffu, w_nn, 0);
+    // short queue: the list is longest-first and every warp takes the next item when it is free (LPT).  Reserving
+    // items ahead of time (records prefetched two deep with cp.async) was measured and dropped: it hands a warp
+    // two of the longest items back to back (the launch doubled), and restricted to the short classes it bought
+    // nothing (0.219 vs 0.207 ms) — the four warps of a sub-partition already overlap each other's item boundaries.
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0) w = atomicAdd(g.item_count + kQShortCtr, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_items) break;
+        const uint4 rec = g.recs[(size_t)w * 32 + lane];
+        item_run(g, w, rec, lane, warp_smem);
     }
 }
 
