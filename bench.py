@@ -509,35 +509,44 @@ def run_ours(args):
     step_no = [0]
 
     def overlapped_steps(k):
-        """N > 1, NCCL path: K steps whose all-gather runs on a side stream, overlapped with the next step's solve
-        (double-buffered winner / gathered blocks: step k + 1 never touches what the gather of step k reads or
-        writes).  Returns the device time from the start of the first step to the completion of the last gather,
-        divided evenly over the steps (CUDA events on the engine's stream, which waits for the side stream)."""
+        """N > 1, NCCL path: the all-gather of step i runs on a side stream DURING the solve of step i + 1
+        (double-buffered winner / gathered blocks).  Timing stays per step with CUDA events on the engine's stream:
+        the gather of step i is released only after the L2 flush that precedes step i + 1 (so it cannot hide in the
+        untimed flush) and step i + 1's closing event waits for it, i.e. every gather lies inside a timed interval;
+        the last step's gather is a timed tail added to the last step."""
+        evs = []
+        prev = None
         with torch.cuda.stream(ext):
-            e0 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(k):
-                b = step_no[0] & 1
-                step_no[0] += 1
-                flush.fill_(1)
-                eng.grid_solve_device(grid, blocks[b][1])
-                done = torch.cuda.Event()
-                done.record(ext)
-                comm_stream.wait_event(done)
+            def release_gather(b):
+                go = torch.cuda.Event()
+                go.record(ext)
+                comm_stream.wait_event(go)
                 with torch.cuda.stream(comm_stream):
                     dist.all_gather_into_tensor(gathered[b], blocks[b][0])
                     gone = torch.cuda.Event()
                     gone.record(comm_stream)
-                pending[b] = gone
-                nb = step_no[0] & 1
-                if pending[nb] is not None:
-                    ext.wait_event(pending[nb])  # block nb is free again once its gather has finished
-            ext.wait_stream(comm_stream)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record()
+                return gone
+            for _ in range(k):
+                b = step_no[0] & 1
+                step_no[0] += 1
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                gone = release_gather(prev) if prev is not None else None
+                eng.grid_solve_device(grid, blocks[b][1])
+                if gone is not None:
+                    ext.wait_event(gone)
+                e1.record()
+                evs.append((e0, e1))
+                prev = b
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            ext.wait_event(release_gather(prev))
+            t1.record()
         torch.cuda.synchronize()
-        return [e0.elapsed_time(e1) / k] * k
-    pending = [None, None]
+        ms = [a.elapsed_time(b) for a, b in evs]
+        ms[-1] += t0.elapsed_time(t1)
+        return ms
     overlap = world > 1 and xchg is None and not os.environ.get("WVA_BENCH_NO_OVERLAP")
     run_steps = overlapped_steps if overlap else timed_steps
 
