@@ -479,6 +479,10 @@ int size_depth_for(int n) {
 }
 int run_size_rounds(wva_handle* h, const SizeArgs& sa, int n) {
     const int D = size_depth_for(n);
+    int size_rev = 1;  // solver returns to the block vote after a per-step excursion (0 = stays on the per-step path)
+    if (const char* e = getenv("WVA_SIZE_REV")) size_rev = atoi(e);
+    int dbg_round = -1;  // diagnostics: record per-request SM cycles of this round's sz2_solve (wva_dbg_read_size)
+    if (const char* e = getenv("WVA_SIZE_DBG_ROUND")) dbg_round = atoi(e);
     const size_t per_cand = 2 * ((size_t)(1 << D) - 1 + 2);  // two searches: a tree each, plus the two end points
     const size_t cap = per_cand * (size_t)n;                 // requests per round, worst case
     const size_t n2 = 2 * (size_t)n;
@@ -551,7 +555,15 @@ int run_size_rounds(wva_handle* h, const SizeArgs& sa, int n) {
             sz2_sort_local<<<cks, kSortThreads, 0, h->stream>>>(g);
             ws_items_scan<<<1, 256, 0, h->stream>>>(g.ws);
             ws_items_scatter<<<items_blocks, 256, 0, h->stream>>>(g.ws);
-            sz2_solve<<<solve_blocks, 256, 0, h->stream>>>(g);
+            g.dbg = nullptr;
+            if (dbg_round == round + r) {
+                CK(h->d_dbg.ensure(16 * cap));
+                CK(cudaMemsetAsync(h->d_dbg.p, 0, 16 * cap, h->stream));
+                g.dbg = (unsigned*)h->d_dbg.p;
+                h->dbg_n = cap;
+            }
+            if (size_rev) sz2_solve<1><<<solve_blocks, 256, 0, h->stream>>>(g);
+            else sz2_solve<0><<<solve_blocks, 256, 0, h->stream>>>(g);
             h->launches += 6;
         }
         // candidates still unfinished after the group's last advance decide whether another group is needed
@@ -1837,6 +1849,21 @@ int wva_dbg_enable_cycles(wva_handle* h, int on) {
     if (!h) return WVA_ERR_BAD_ARG;
     h->dbg_cycles = on != 0;
     return WVA_OK;
+}
+int wva_dbg_szcnt(unsigned long long* out24, int reset) {
+#ifdef WVA_SZCNT
+    if (reset) { unsigned long long z[24] = {0}; return (int)cudaMemcpyToSymbol(wva::wva_szcnt, z, sizeof(z)); }
+    return (int)cudaMemcpyFromSymbol(out24, wva::wva_szcnt, sizeof(unsigned long long) * 24);
+#else
+    (void)out24; (void)reset;
+    return -1;
+#endif
+}
+long long wva_dbg_read_size(wva_handle* h, unsigned* out4, long long cap) {  // rows of {cycles, N | kind << 16, lambda bits, warp}
+    if (!h || !h->d_dbg.p) return 0;
+    const long long n = std::min<long long>((long long)h->dbg_n, cap);
+    cudaMemcpy(out4, h->d_dbg.p, 16 * n, cudaMemcpyDeviceToHost);
+    return n;
 }
 long long wva_dbg_read_cycles(wva_handle* h, unsigned* cycles, unsigned* cells, long long cap) {
     if (!h || !h->d_dbg.p) return 0;

@@ -190,6 +190,14 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // state j, one 8-byte column per lane) and pass 2 reads them back instead of re-running the
 // recurrence for those states — most grid chains are shorter than that.
 //
+#ifdef WVA_SZCNT  // diagnostics build (tools/size_dbg.py): which loop the full-length N = 256 chains spend their steps in
+__device__ unsigned long long wva_szcnt[24];
+#define WVA_CNT(k) ++cnt_[k]
+#define WVA_CNT_ADD(k, v) cnt_[k] += (v)
+#else
+#define WVA_CNT(k)
+#define WVA_CNT_ADD(k, v)
+#endif
 #ifdef WVA_PROF  // diagnostics build (tools/prof_chain.py): phase clocks and counters of the last solve
 __device__ long long wva_prof[16];
 #define WVA_PROF_T(k) wva_prof[k] = clock64()
@@ -223,6 +231,9 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     const unsigned warp_mask = __activemask();
     const double lam = (double)lambda;
     const int nh = N - 1;
+#ifdef WVA_SZCNT
+    unsigned cnt_[16] = {0};
+#endif
     Recip A, B;  // reciprocal triples of two consecutive steps (software-pipelined table loads)
     // staged head: full warp, one table.  Everything the solve reads from the table is requested here in one
     // batch: the first 64-entry window, the lane's tail entry (T stays in registers for the whole solve) and
@@ -400,7 +411,12 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             //    chains spend 10/11 of their steps;
             //  * generic 4-step blocks otherwise.
             for (;;) {
+                WVA_CNT(8); WVA_CNT_ADD(9, __popc(__activemask()));
+                if (!(n > nh + 1)) WVA_CNT(4);
+                if (!(n + 16 <= n_stop)) WVA_CNT(5);
+                if (!WVA_FASTWIN(p, blk16_lo, blk16_span)) WVA_CNT(6);
                 if (__all_sync(__activemask(), n > nh + 1 && n >= STASH && n + 16 <= n_stop && WVA_FASTWIN(p, blk16_lo, blk16_span))) {
+                    WVA_CNT(0);
                     const double cA = __dmul_rn(lam, A.yl);
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
@@ -412,6 +428,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 }
                 if (__all_sync(__activemask(), n + 4 <= n_stop && WVA_FASTWIN(p, blk_lo, blk_span))) {
                     if (n < nh) prefetch_l1(tab + 4 * (n + PF));
+                    WVA_CNT(1);
                     WVA_P1_STEP(A)
                     WVA_P1_STEP(B)
                     WVA_P1_STEP(A)
@@ -426,6 +443,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             for (int rv = 0; REV == 0 || rv < REV; ++rv) {
                 if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) goto p1_slow;
                 if (n < nh) prefetch_l1(tab + 4 * (n + PF));
+                WVA_CNT(2);
                 WVA_P1_STEP(A)
                 if (n >= n_stop || !WVA_FASTWIN(p, lo_eff, span_eff)) goto p1_slow;
                 WVA_P1_STEP(B)
@@ -435,6 +453,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         p1_slow:
             if (n >= n_stop) break;
             // p[n] is outside the fast window
+            WVA_CNT(3);
             const unsigned hp = (unsigned)__double2hiint(p);
             if (hp < thr_hi && (n >= nh ? tail_mono : rate_below(lambda, tab_suffix_min(tab, n)))) {
                 j_end = n + 1;  // negligible and past the mode: states > n contribute nothing
@@ -619,7 +638,10 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
         ++i;                                                                \
     }
             for (;;) {  // block phase, as in pass 1; pure-tail also needs i > N (sumP complete)
+                if (!(i + 16 <= j_end)) WVA_CNT(14);
+                if (!WVA_FASTWIN(p, blk16_lo, blk16_span)) WVA_CNT(15);
                 if (__all_sync(__activemask(), i > nh + 1 && i > N && i + 16 <= j_end && WVA_FASTWIN(p, blk16_lo, blk16_span))) {
+                    WVA_CNT(10);
                     const double cA = __dmul_rn(lam, A.yl);
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
@@ -633,6 +655,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 }
                 if (__all_sync(__activemask(), i + 4 <= j_end && WVA_FASTWIN(p, blk2_lo, blk2_span))) {
                     if (i < nh) prefetch_l1(tab + 4 * (i + PF));
+                    WVA_CNT(11);
                     WVA_P2_STEP(A)
                     WVA_P2_STEP(B)
                     WVA_P2_STEP(A)
@@ -644,6 +667,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             for (int rv = 0; REV == 0 || rv < REV; ++rv) {  // per-step phase (see pass 1)
                 if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) goto p2_slow;
                 if (i < nh) prefetch_l1(tab + 4 * (i + PF));
+                WVA_CNT(12);
                 WVA_P2_STEP(A)
                 if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) goto p2_slow;
                 WVA_P2_STEP(B)
@@ -686,6 +710,14 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     if (w < 0.0f) w = 0.0f;
     st.avg_wait_time = w;
 #undef WVA_LOAD_TAIL
+#ifdef WVA_SZCNT
+    if (N == 256 && j_end > K - 16) {  // full-length chains of the largest batch size only
+        for (int k = 0; k < 16; ++k) if (cnt_[k]) atomicAdd(&wva_szcnt[k], (unsigned long long)cnt_[k]);
+        atomicAdd(&wva_szcnt[16], 1ull);
+        atomicAdd(&wva_szcnt[17], (unsigned long long)(blk16_span != 0));
+        atomicAdd(&wva_szcnt[18], (unsigned long long)nh);
+    }
+#endif
     return bail ? kSolveBail : kSolveOk;
 }
 
@@ -818,10 +850,9 @@ __device__ __forceinline__ int solve_shared(const double* __restrict__ tab, int 
     return solve_shared_t<0>(tab, N, K, lambda, st, nullptr);
 }
 // Per-lane private tables (size path): every lane streams its own table, so prefetch much further ahead.
+template <int REV>
 __device__ __forceinline__ int solve_private(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st) {
-    // lanes with private tables rarely agree on a block again once one of them left it: stay on the
-    // per-step path (REV = 0; measured on config 4: 27.6 ms against 31.0 ms with REV = 1)
-    return solve_shared_t<0, 48, false, 0>(tab, N, K, lambda, st, nullptr);
+    return solve_shared_t<0, 48, false, REV>(tab, N, K, lambda, st, nullptr);
 }
 
 // Stored-vector fallback: a literal restatement of computeProbabilities /
