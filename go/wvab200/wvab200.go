@@ -11,6 +11,7 @@
 //   - Engine.Upload / UpdateLoad / Resolve: the streaming reconcile (fleet resident on the GPU, only the load
 //     columns travel per tick: wva_upload / wva_update_load / wva_resolve)
 //   - Engine.Summarize: System.AllocateByType + Solver.Solve's allocation diffs (wva_summarize).
+//   - Engine.MM1K: analyzer.MM1KModel (closed form) for arrays of (K, lambda, mu) (wva_mm1k_solve).
 // tests/c_abi/solve_smoke.c drives the same entry points from compiled C.
 package wvab200
 
@@ -450,6 +451,50 @@ func (e *Engine) Resolve(r *Resident) (*config.AllocationSolution, error) {
 type TypeTotal struct {
 	Count, Limit int
 	Cost         float32
+}
+
+// MM1KStats mirrors the statistics of analyzer.MM1KModel after Solve (pkg/analyzer/queuemodel.go:10-19).
+type MM1KStats struct {
+	IsValid                                                                                     bool
+	Rho, AvgNumInSystem, Throughput, AvgRespTime, AvgServTime, AvgWaitTime, AvgQueueLength float32
+}
+
+// MM1K evaluates analyzer.MM1KModel (closed form, pkg/analyzer/mm1kmodel.go) for n (K, lambda, mu) triples
+// on the device (wva_mm1k_solve).
+func (e *Engine) MM1K(K []int32, lambda, mu []float32) ([]MM1KStats, error) {
+	n := len(K)
+	if len(lambda) != n || len(mu) != n {
+		return nil, fmt.Errorf("wva_mm1k_solve: K, lambda, mu must have one length")
+	}
+	if n == 0 {
+		return nil, nil
+	}
+	valid := make([]uint8, n)
+	cols := make([][]float32, 7)
+	for i := range cols {
+		cols[i] = make([]float32, n)
+	}
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	var out C.wva_mm1k_out
+	out.is_valid = u8p(valid)
+	out.rho, out.avg_num_in_system, out.throughput, out.avg_resp_time = f32p(cols[0]), f32p(cols[1]), f32p(cols[2]), f32p(cols[3])
+	out.avg_serv_time, out.avg_wait_time, out.avg_queue_length = f32p(cols[4]), f32p(cols[5]), f32p(cols[6])
+	pin.Pin(unsafe.Pointer(out.is_valid))
+	for _, p := range []*C.float{out.rho, out.avg_num_in_system, out.throughput, out.avg_resp_time, out.avg_serv_time,
+		out.avg_wait_time, out.avg_queue_length} {
+		pin.Pin(unsafe.Pointer(p))
+	}
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if rc := C.wva_mm1k_solve(e.h, C.int32_t(n), i32p(K), f32p(lambda), f32p(mu), &out); rc != C.WVA_OK {
+		return nil, e.fail("wva_mm1k_solve", rc)
+	}
+	res := make([]MM1KStats, n)
+	for i := range res {
+		res[i] = MM1KStats{valid[i] != 0, cols[0][i], cols[1][i], cols[2][i], cols[3][i], cols[4][i], cols[5][i], cols[6][i]}
+	}
+	return res, nil
 }
 
 // Diff mirrors core.AllocationDiff (pkg/core/allocation.go:344-350); accelerator "none" = no allocation.

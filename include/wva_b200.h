@@ -274,6 +274,31 @@ typedef struct wva_summary {
  * stay resident until the next call).  WVA_ERR_STATE when there is none. */
 int wva_summarize(wva_handle *h, wva_summary *out);
 
+/* ---- MM1KModel (closed form) --------------------------------------------- */
+
+/*
+ * MM1KModel.Solve for n independent (K, lambda, mu) triples: pkg/analyzer/mm1kmodel.go:19-92 over
+ * QueueModel.Solve (queuemodel.go:27-37).  The reference keeps this model next to the state-dependent one but
+ * does not call it on the production path; it is here so that every model of pkg/analyzer has a device function.
+ * One thread per triple, p[] is streamed (never stored).  math.Pow is restated from the Go standard library's
+ * binary-powering algorithm (integer exponents only occur) so that host oracle and device agree bit for bit; it is
+ * not pinned against the Go binary (no Go toolchain here), see DESIGN.md.
+ * Columns have n entries (host pointers, any may be NULL); entries of an invalid triple are 0 except rho.
+ */
+typedef struct wva_mm1k_out {
+    uint8_t *is_valid;
+    float *rho;
+    float *avg_num_in_system;
+    float *throughput;
+    float *avg_resp_time;
+    float *avg_serv_time;
+    float *avg_wait_time;
+    float *avg_queue_length;
+    double *sum_p; /* sum of the state probabilities as the reference accumulates it */
+} wva_mm1k_out;
+int wva_mm1k_solve(wva_handle *h, int32_t n, const int32_t *K, const float *lambda, const float *mu,
+                   wva_mm1k_out *out);
+
 /* ---- streaming reconcile (BASELINE config 5) ---------------------------- */
 
 /* Make `fleet` resident on the device (copies everything; caller memory is not

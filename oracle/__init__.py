@@ -96,6 +96,8 @@ def lib():
     L.wvao_mm1k_solve.argtypes = [vp, f, f, C.POINTER(ModelStats)]
     L.wvao_mm1k_probs.restype = C.POINTER(C.c_double)
     L.wvao_mm1k_probs.argtypes = [vp]
+    L.wvao_go_pow_uint.restype = C.c_double
+    L.wvao_go_pow_uint.argtypes = [C.c_double, C.c_int64]
     L.wvao_model_new_rates.restype = vp
     L.wvao_model_new_rates.argtypes = [i, C.POINTER(C.c_float), i]
     L.wvao_analyzer_new.restype = vp
@@ -251,6 +253,32 @@ class MM1K:
 
     def probs(self):
         return np.ctypeslib.as_array(lib().wvao_mm1k_probs(self._h), (self.K + 1,)).copy()
+
+
+def go_pow_uint(x: float, n: int) -> float:
+    """math.Pow(x, float64(n)) for an integer n >= 0, as restated from the Go standard library."""
+    return float(lib().wvao_go_pow_uint(float(x), int(n)))
+
+
+def mm1k_solve(K, lam, mu) -> dict:
+    """MM1KModel.Solve for arrays of (K, lambda, mu): dict of numpy columns (the oracle of wva_mm1k_solve)."""
+    K = np.asarray(K, np.int32)
+    lam = np.asarray(lam, np.float32)
+    mu = np.asarray(mu, np.float32)
+    names = ("rho", "avg_num_in_system", "throughput", "avg_resp_time", "avg_serv_time", "avg_wait_time",
+             "avg_queue_length")
+    out = {n: np.zeros(K.size, np.float32) for n in names}
+    out["is_valid"] = np.zeros(K.size, np.uint8)
+    out["sum_p"] = np.zeros(K.size, np.float64)
+    for i in range(K.size):
+        st = MM1K(int(K[i])).solve(float(lam[i]), float(mu[i]))
+        out["is_valid"][i] = st["is_valid"]
+        out["rho"][i] = st["rho"]
+        if st["is_valid"]:
+            for n in names[1:]:
+                out[n][i] = st[n]
+            out["sum_p"][i] = st["sum_p"]
+    return out
 
 
 def binary_search(xmin, xmax, ytarget, fn):

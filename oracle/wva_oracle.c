@@ -143,6 +143,66 @@ int wvao_binary_search(float xmin, float xmax, float ytarget, wvao_eval_fn eval,
 /* path; restated for the reference's model tests)                          */
 /* ------------------------------------------------------------------------ */
 
+/* math.Pow for a non-negative integer exponent, restated from the Go standard library's pure-Go implementation
+ * (src/math/pow.go, the only one amd64 has): special cases, then binary powering on the Frexp mantissa with the
+ * exponent carried in an integer, then Ldexp.  Every operation is an IEEE double multiply/add or exact bit
+ * manipulation, so the CUDA restatement (wva_device.cuh: go_pow_uint) produces the same bits.  The Go toolchain is
+ * absent here: this follows the published algorithm and is NOT pinned against the Go binary; the test suite checks it
+ * against libm's pow to a few ulp (tests/test_mm1k.py). */
+static double go_ldexp(double frac, int64_t e) { /* src/math/ldexp.go */
+    if (frac == 0 || isinf(frac) || isnan(frac)) return frac;
+    uint64_t x;
+    memcpy(&x, &frac, 8);
+    int64_t ex = (int64_t)((x >> 52) & 0x7ff);
+    if (ex == 0) { /* normalize a subnormal */
+        frac *= 4503599627370496.0; /* 2^52 */
+        memcpy(&x, &frac, 8);
+        ex = (int64_t)((x >> 52) & 0x7ff) - 52;
+    }
+    e += ex - 1023;
+    if (e < -1075) return copysign(0.0, frac);
+    if (e > 1023) return frac < 0 ? -INFINITY : INFINITY;
+    double m = 1.0;
+    if (e < -1022) { /* denormal result: one rounding, in the final multiply */
+        e += 53;
+        m = 1.0 / 9007199254740992.0; /* 2^-53 */
+    }
+    x &= ~((uint64_t)0x7ff << 52);
+    x |= (uint64_t)(e + 1023) << 52;
+    double r;
+    memcpy(&r, &x, 8);
+    return m * r;
+}
+double wvao_go_pow_uint(double x, int64_t n) { /* math.Pow(x, float64(n)), n >= 0 */
+    if (n == 0 || x == 1) return 1;
+    if (n == 1) return x;
+    if (isnan(x)) return x;
+    if (x == 0) return (n & 1) ? x : 0.0; /* y > 0: +-0 for odd y, +0 otherwise */
+    if (isinf(x)) return (x < 0 && (n & 1)) ? -INFINITY : INFINITY;
+    double a1 = 1.0;
+    int64_t ae = 0;
+    int xe_i;
+    double x1 = frexp(x, &xe_i); /* exact; frac in [0.5, 1) */
+    int64_t xe = xe_i;
+    for (int64_t i = n; i != 0; i >>= 1) {
+        if (xe < -(1 << 12) || (1 << 12) < xe) { /* catastrophic over/underflow: Ldexp settles it */
+            ae += xe;
+            break;
+        }
+        if (i & 1) {
+            a1 *= x1;
+            ae += xe;
+        }
+        x1 *= x1;
+        xe <<= 1;
+        if (x1 < .5) {
+            x1 += x1;
+            xe--;
+        }
+    }
+    return go_ldexp(a1, ae);
+}
+
 struct wvao_mm1k {
     int K;
     double *p;
@@ -181,12 +241,12 @@ void wvao_mm1k_solve(wvao_mm1k *m, float lambda, float mu, wvao_model_stats *out
         if (s->rho == 1) {
             m->p[0] = 1 / (double)(m->K + 1);
         } else {
-            m->p[0] = (1 - (double)s->rho) / (1 - pow((double)s->rho, (double)(m->K + 1)));
+            m->p[0] = (1 - (double)s->rho) / (1 - wvao_go_pow_uint((double)s->rho, (int64_t)m->K + 1));
         }
         m->sum_p = 0;
         double p0 = m->p[0];
         for (int i = 0; i <= m->K; i++) {
-            m->p[i] = p0 * pow((double)s->rho, (double)i);
+            m->p[i] = p0 * wvao_go_pow_uint((double)s->rho, (int64_t)i);
             m->sum_p += m->p[i];
         }
         double temp = 0;

@@ -80,6 +80,8 @@ wvao_mm1k *wvao_mm1k_new(int K);
 void wvao_mm1k_free(wvao_mm1k *m);
 void wvao_mm1k_solve(wvao_mm1k *m, float lambda, float mu, wvao_model_stats *out);
 const double *wvao_mm1k_probs(const wvao_mm1k *m);
+/* math.Pow(x, n) for an integer n >= 0 as the Go standard library computes it (src/math/pow.go) */
+double wvao_go_pow_uint(double x, int64_t n);
 
 /* NewQueueAnalyzer / BuildModel: queueanalyzer.go:87-131. NULL on check() failure. */
 wvao_analyzer *wvao_analyzer_new(int max_batch, int max_queue, float alpha, float beta, float gamma,

@@ -32,6 +32,7 @@ SAT_BY_NAME = {  # pkg/config/config.go:28-41
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
 i64p = C.POINTER(C.c_int64)
+f64p = C.POINTER(C.c_double)
 u8p = C.POINTER(C.c_uint8)
 
 
@@ -112,8 +113,14 @@ class SummaryC(C.Structure):
                 ("diff_new_replicas", i32p), ("diff_cost", f32p)]
 
 
+class Mm1kOutC(C.Structure):
+    _fields_ = [("is_valid", u8p), ("rho", f32p), ("avg_num_in_system", f32p), ("throughput", f32p),
+                ("avg_resp_time", f32p), ("avg_serv_time", f32p), ("avg_wait_time", f32p),
+                ("avg_queue_length", f32p), ("sum_p", f64p)]
+
+
 _CT = {np.dtype(np.float32): C.c_float, np.dtype(np.int32): C.c_int32, np.dtype(np.uint8): C.c_uint8,
-       np.dtype(np.int64): C.c_int64}
+       np.dtype(np.int64): C.c_int64, np.dtype(np.float64): C.c_double}
 
 
 def ptr(a: np.ndarray):

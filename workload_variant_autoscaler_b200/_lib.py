@@ -38,7 +38,7 @@ EXPORTS = (
     "wva_tunables_default", "wva_create", "wva_destroy", "wva_strerror", "wva_last_error", "wva_abi_version",
     "wva_analyze", "wva_solve", "wva_grid_solve", "wva_sweep", "wva_upload", "wva_update_load", "wva_resolve",
     "wva_grid_solve_device", "wva_resolve_device", "wva_stream", "wva_synchronize", "wva_launch_count",
-    "wva_last_kernel_ms", "wva_last_device_ms", "wva_summarize", "wva_solve_greedy",
+    "wva_last_kernel_ms", "wva_last_device_ms", "wva_summarize", "wva_solve_greedy", "wva_mm1k_solve",
     "wva_xchg_create", "wva_xchg_open", "wva_xchg_publish", "wva_xchg_error", "wva_xchg_destroy",
 )
 
@@ -77,6 +77,7 @@ def lib():
         ("wva_synchronize", [vp]),
         ("wva_solve_greedy", [C.POINTER(_abi.FleetC), C.POINTER(_abi.AllocsC), C.POINTER(_abi.AllocsC)]),
         ("wva_summarize", [vp, C.POINTER(_abi.SummaryC)]),
+        ("wva_mm1k_solve", [vp, i32, i32p, f32p, f32p, C.POINTER(_abi.Mm1kOutC)]),
         ("wva_xchg_create", [vp, C.c_int, C.c_int, C.c_size_t, C.c_void_p]),
         ("wva_xchg_open", [vp, C.c_int, C.c_void_p]),
         ("wva_xchg_publish", [vp, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),

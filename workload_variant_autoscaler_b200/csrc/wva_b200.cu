@@ -1662,6 +1662,59 @@ int wva_summarize(wva_handle* h, wva_summary* out) {
     return WVA_OK;
 }
 
+// MM1KModel.Solve for n triples (include/wva_b200.h).
+int wva_mm1k_solve(wva_handle* h, int32_t n, const int32_t* K, const float* lambda, const float* mu, wva_mm1k_out* out) {
+    if (!h || !out || n < 0 || (n > 0 && (!K || !lambda || !mu))) return WVA_ERR_BAD_ARG;
+    if (n == 0) return WVA_OK;
+    for (int i = 0; i < n; ++i)
+        if (K[i] < 0) return h->fail(WVA_ERR_BAD_ARG, "MM1K: negative K");  // NewMM1KModel returns nil (mm1kmodel.go:20-22)
+    CK(cudaSetDevice(h->device));
+    const size_t N = (size_t)n;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 16); return at; };
+    const size_t i_K = take(4 * N), i_lam = take(4 * N), i_mu = take(4 * N);
+    const size_t in_bytes = o;
+    const size_t o_sum = take(8 * N), o_valid = take(N), o_rho = take(4 * N), o_nsys = take(4 * N), o_thr = take(4 * N),
+                 o_resp = take(4 * N), o_serv = take(4 * N), o_wait = take(4 * N), o_qlen = take(4 * N);
+    CK(h->d_summary.ensure(o));
+    CK(h->out_stage.ensure(o));
+    char* d = (char*)h->d_summary.p;
+    char* hs = (char*)h->out_stage.p;
+    memcpy(hs + i_K, K, 4 * N);
+    memcpy(hs + i_lam, lambda, 4 * N);
+    memcpy(hs + i_mu, mu, 4 * N);
+    CK(cudaMemcpyAsync(d, hs, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    Mm1kArgs g;
+    g.n = n;
+    g.K = (const int*)(d + i_K);
+    g.lambda = (const float*)(d + i_lam);
+    g.mu = (const float*)(d + i_mu);
+    g.sum_p = (double*)(d + o_sum);
+    g.is_valid = (uint8_t*)(d + o_valid);
+    g.rho = (float*)(d + o_rho);
+    g.avg_num_in_system = (float*)(d + o_nsys);
+    g.throughput = (float*)(d + o_thr);
+    g.avg_resp_time = (float*)(d + o_resp);
+    g.avg_serv_time = (float*)(d + o_serv);
+    g.avg_wait_time = (float*)(d + o_wait);
+    g.avg_queue_length = (float*)(d + o_qlen);
+    mm1k_kernel<<<(unsigned)((N + 127) / 128), 128, 0, h->stream>>>(g);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hs + in_bytes, d + in_bytes, o - in_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (out->sum_p) memcpy(out->sum_p, hs + o_sum, 8 * N);
+    if (out->is_valid) memcpy(out->is_valid, hs + o_valid, N);
+    if (out->rho) memcpy(out->rho, hs + o_rho, 4 * N);
+    if (out->avg_num_in_system) memcpy(out->avg_num_in_system, hs + o_nsys, 4 * N);
+    if (out->throughput) memcpy(out->throughput, hs + o_thr, 4 * N);
+    if (out->avg_resp_time) memcpy(out->avg_resp_time, hs + o_resp, 4 * N);
+    if (out->avg_serv_time) memcpy(out->avg_serv_time, hs + o_serv, 4 * N);
+    if (out->avg_wait_time) memcpy(out->avg_wait_time, hs + o_wait, 4 * N);
+    if (out->avg_queue_length) memcpy(out->avg_queue_length, hs + o_qlen, 4 * N);
+    return WVA_OK;
+}
+
 int wva_sweep(wva_handle* h, const wva_fleet* fleet, int32_t n_rates, wva_sweep_out* out) {
     if (!h || !out || n_rates < 1) return WVA_ERR_BAD_ARG;
     if (!out->valid || !out->rate || !out->ttft || !out->itl || !out->throughput || !out->rho)

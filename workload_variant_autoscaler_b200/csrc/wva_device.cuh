@@ -12,6 +12,7 @@
 // quotient — the same bits as the reference's DIVSD — in 4 dependent FP64 ops instead
 // of the ~10-op generic division sequence (see DESIGN.md "Exact division").
 #pragma once
+#include <math_constants.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -113,6 +114,68 @@ __device__ __forceinline__ double step_recip(double p, double lam, double c, con
     const double q0 = __fma_rn(a, r.yh, t);
     const double res = __fma_rn(-r.b, q0, a);
     return __fma_rn(res, r.yh, q0);
+}
+
+// math.Pow(x, n) for an integer n >= 0 as the Go standard library computes it (src/math/pow.go: binary powering on
+// the Frexp mantissa, exponent carried in an integer, Ldexp at the end): IEEE double multiplies / adds and exact bit
+// manipulation only, so a host restatement of the same algorithm gives the same bits (that is how the tests check it).
+// Used by the closed-form MM1KModel only.
+__device__ __forceinline__ double go_ldexp(double frac, long long e) {
+    if (frac == 0.0 || isinf(frac) || isnan(frac)) return frac;
+    unsigned long long x = (unsigned long long)__double_as_longlong(frac);
+    long long ex = (long long)((x >> 52) & 0x7ffull);
+    if (ex == 0) {
+        frac = __dmul_rn(frac, 4503599627370496.0);
+        x = (unsigned long long)__double_as_longlong(frac);
+        ex = (long long)((x >> 52) & 0x7ffull) - 52;
+    }
+    e += ex - 1023;
+    if (e < -1075) return copysign(0.0, frac);
+    if (e > 1023) return frac < 0.0 ? -CUDART_INF : CUDART_INF;
+    double m = 1.0;
+    if (e < -1022) {
+        e += 53;
+        m = 1.0 / 9007199254740992.0;
+    }
+    x &= ~(0x7ffull << 52);
+    x |= (unsigned long long)(e + 1023) << 52;
+    return __dmul_rn(m, __longlong_as_double((long long)x));
+}
+__device__ __forceinline__ double go_pow_uint(double x, long long n) {
+    if (n == 0 || x == 1.0) return 1.0;
+    if (n == 1) return x;
+    if (isnan(x)) return x;
+    if (x == 0.0) return (n & 1) ? x : 0.0;
+    if (isinf(x)) return (x < 0.0 && (n & 1)) ? -CUDART_INF : CUDART_INF;
+    double a1 = 1.0;
+    long long ae = 0;
+    // Frexp: mantissa in [0.5, 1), exact
+    unsigned long long xb = (unsigned long long)__double_as_longlong(x);
+    long long xe = (long long)((xb >> 52) & 0x7ffull);
+    if (xe == 0) {  // subnormal: normalise first
+        const double xn = __dmul_rn(x, 4503599627370496.0);
+        xb = (unsigned long long)__double_as_longlong(xn);
+        xe = (long long)((xb >> 52) & 0x7ffull) - 52;
+    }
+    xe -= 1022;
+    double x1 = __longlong_as_double((long long)((xb & ~(0x7ffull << 52)) | (1022ull << 52)));
+    for (long long i = n; i != 0; i >>= 1) {
+        if (xe < -(1 << 12) || (1 << 12) < xe) {
+            ae += xe;
+            break;
+        }
+        if (i & 1) {
+            a1 = __dmul_rn(a1, x1);
+            ae += xe;
+        }
+        x1 = __dmul_rn(x1, x1);
+        xe <<= 1;
+        if (x1 < 0.5) {
+            x1 = __dadd_rn(x1, x1);
+            xe--;
+        }
+    }
+    return go_ldexp(a1, ae);
 }
 
 // Exponent windows (high 32 bits of the double).  p in [2^-280, 2^600) keeps every

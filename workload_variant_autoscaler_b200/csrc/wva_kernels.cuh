@@ -1553,6 +1553,61 @@ __global__ void __launch_bounds__(256) summary_kernel(DevFleet f, AllocCols win,
 }
 
 // ---------------------------------------------------------------------------
+// MM1KModel (closed form): pkg/analyzer/mm1kmodel.go:19-92 over QueueModel.Solve (queuemodel.go:27-37).  One
+// thread per (K, lambda, mu) triple; the probabilities are streamed in the reference's order (sumP and the
+// sum(i p[i]) accumulate over i = 0..K), never stored.
+// ---------------------------------------------------------------------------
+struct Mm1kArgs {
+    int n;
+    const int* K;
+    const float* lambda;
+    const float* mu;
+    uint8_t* is_valid;
+    float *rho, *avg_num_in_system, *throughput, *avg_resp_time, *avg_serv_time, *avg_wait_time, *avg_queue_length;
+    double* sum_p;
+};
+__global__ void __launch_bounds__(128) mm1k_kernel(Mm1kArgs g) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= g.n) return;
+    const int K = g.K[q];
+    const float lambda = g.lambda[q], mu = g.mu[q];
+    const float rho = (lambda == mu) ? 1.0f : __fdiv_rn(lambda, mu);  // ComputeRho: mm1kmodel.go:38-44
+    // QueueModel.Solve validity: queuemodel.go:31 with GetRhoMax = K (mm1kmodel.go:46-48)
+    const bool valid = !((rho < 0.0f) || (rho >= (float)K) || (lambda < 0.0f) || (mu <= 0.0f));
+    float nsys = 0.f, thr = 0.f, resp = 0.f, serv = 0.f, wait = 0.f, qlen = 0.f;
+    double sum_p = 0.0;
+    if (valid) {
+        const double r = (double)rho;
+        // computeProbabilities: mm1kmodel.go:51-72
+        const double p0 = (rho == 1.0f) ? __ddiv_rn(1.0, (double)(K + 1))
+                                        : __ddiv_rn(__dsub_rn(1.0, r), __dsub_rn(1.0, go_pow_uint(r, (long long)K + 1)));
+        double temp = 0.0, pK = 0.0;
+        for (int i = 0; i <= K; ++i) {
+            const double pi = __dmul_rn(p0, go_pow_uint(r, (long long)i));
+            sum_p = __dadd_rn(sum_p, pi);
+            temp = __dadd_rn(temp, __dmul_rn((double)i, pi));  // computeStatistics: :75-92
+            pK = pi;
+        }
+        nsys = (float)temp;
+        thr = __fmul_rn(lambda, __fsub_rn(1.0f, (float)pK));
+        resp = __fdiv_rn(nsys, thr);
+        serv = __fdiv_rn(1.0f, mu);
+        wait = __fsub_rn(resp, serv);
+        if (wait < 0.0f) wait = 0.0f;
+        qlen = __fmul_rn(thr, wait);
+    }
+    g.is_valid[q] = valid ? 1 : 0;
+    g.rho[q] = rho;
+    g.avg_num_in_system[q] = nsys;
+    g.throughput[q] = thr;
+    g.avg_resp_time[q] = resp;
+    g.avg_serv_time[q] = serv;
+    g.avg_wait_time[q] = wait;
+    g.avg_queue_length[q] = qlen;
+    g.sum_p[q] = sum_p;
+}
+
+// ---------------------------------------------------------------------------
 // Latency sweep: warp = 32 consecutive rates of one (server, acc) pair.
 // ---------------------------------------------------------------------------
 struct SweepArgs {

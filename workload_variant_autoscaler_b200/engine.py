@@ -175,6 +175,26 @@ class Engine:
         self._check(self._L.wva_summarize(self._h, C.byref(sc)))
         return {"by_type": by_type, "diff": diff}
 
+    def mm1k_solve(self, K, lam, mu) -> dict:
+        """``MM1KModel.Solve`` (pkg/analyzer/mm1kmodel.go:19-92) for arrays of (K, lambda, mu) triples; returns the
+        model statistics as numpy columns (``is_valid``, ``rho``, ``avg_num_in_system``, ``throughput``,
+        ``avg_resp_time``, ``avg_serv_time``, ``avg_wait_time``, ``avg_queue_length``, ``sum_p``)."""
+        K = np.ascontiguousarray(K, np.int32)
+        lam = np.ascontiguousarray(lam, np.float32)
+        mu = np.ascontiguousarray(mu, np.float32)
+        if not (K.shape == lam.shape == mu.shape and K.ndim == 1):
+            raise ValueError("K, lam, mu must be 1-D arrays of one length")
+        n = K.size
+        out = {"is_valid": np.zeros(n, np.uint8)}
+        names = ("rho", "avg_num_in_system", "throughput", "avg_resp_time", "avg_serv_time", "avg_wait_time",
+                 "avg_queue_length")
+        for name in names:
+            out[name] = np.zeros(n, np.float32)
+        out["sum_p"] = np.zeros(n, np.float64)
+        oc = _abi.Mm1kOutC(_abi.ptr(out["is_valid"]), *[_abi.ptr(out[name]) for name in names], _abi.ptr(out["sum_p"]))
+        self._check(self._L.wva_mm1k_solve(self._h, n, _abi.ptr(K), _abi.ptr(lam), _abi.ptr(mu), C.byref(oc)))
+        return out
+
     # -- device-resident variants (multi-GPU driver, bench) -------------------
     def grid_solve_device(self, grid: Grid, winners_dev: _abi.AllocsC):
         gc = grid.as_c()
