@@ -64,6 +64,8 @@ def _cases():
     lam = np.concatenate([lam, np.array([e[1] for e in extra], np.float32)])
     mu = np.concatenate([mu, np.array([e[2] for e in extra], np.float32)])
     lam[:200] = mu[:200]  # rho == 1 exactly
+    K[200:600] = rng.integers(0, 3, 400)  # small K: rho >= K makes the model invalid (queuemodel.go:31)
+    lam[600:700] = -lam[600:700]
     return K, lam, mu
 
 
