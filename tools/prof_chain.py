@@ -6,7 +6,7 @@ shutil.copy("tools/var/libwva_prof.so", "workload_variant_autoscaler_b200/libwva
 import oracle
 from workload_variant_autoscaler_b200 import Engine, Grid, synth_fleet
 e = Engine(0); L = e._L
-for ratio, b in ((10, 256), (10, 64), (1, 256)):
+for ratio, b in [(int(a.split(":")[0]), int(a.split(":")[1])) for a in (sys.argv[1:] or ["10:256", "10:64", "1:256"])]:
     f = synth_fleet(1, 1, seed=42)
     f.srv_slo_tps[:] = 0
     f.max_queue_to_batch_ratio = ratio
