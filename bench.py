@@ -173,6 +173,24 @@ def _cpu_worker(args):
     return n
 
 
+_REF = {}
+
+
+def _ref_init():
+    import oracle
+    from workload_variant_autoscaler_b200 import config2_grid, synth_fleet
+    _REF["oracle"] = oracle
+    _REF["fleet"] = synth_fleet(N_MODELS, N_ACC, seed=42)
+    _REF["grid"] = config2_grid(N_BATCH, N_REPLICAS)
+
+
+def _ref_task(task):
+    p, c0, c1 = task
+    per = N_BATCH * N_REPLICAS
+    _REF["oracle"].grid_cells(_REF["fleet"], _REF["grid"], p * per + c0, p * per + c1)
+    return c1 - c0
+
+
 def sample_pairs(n_pairs: int):
     total = N_MODELS * N_ACC
     n_pairs = max(1, min(n_pairs, total))
@@ -229,17 +247,22 @@ def run_reference(args):
 
     import oracle
     oracle.build()
-    cores = min(len(os.sched_getaffinity(0)), 64)
-    pairs_per_step = sample_pairs(max(cores, 8))  # one (model, accelerator) pair = 16384 cells per worker per step
-    chunks = [pairs_per_step[i::cores] for i in range(cores)]
-    chunks = [c for c in chunks if c]
-    per_step_cells = len(pairs_per_step) * N_BATCH * N_REPLICAS
+    cores = len(os.sched_getaffinity(0))  # every logical CPU the process may use
+    # a step = a bounded sample of the workload: 2 x cores (model, accelerator) pairs (all 256 x 64 cells of each),
+    # cut into tasks of 2048 cells that the workers pull one at a time (the cost of a cell varies 100x with the
+    # pair and the rate: static chunks left most workers waiting for the slowest pair)
+    pairs_per_step = sample_pairs(min(max(2 * cores, 16), N_MODELS * N_ACC))
+    per_pair = N_BATCH * N_REPLICAS
+    task_cells = 2048
+    tasks = [(p, c0, min(c0 + task_cells, per_pair)) for p in pairs_per_step for c0 in range(0, per_pair, task_cells)]
+    per_step_cells = len(pairs_per_step) * per_pair
     # one-core rate on a small sample, so that the record shows what the process pool actually gained
     one = cpu_baseline_port(4, reps=3)
     ctx = mp.get_context("fork")
-    with ctx.Pool(len(chunks)) as pool:
+    n_proc = min(cores, len(tasks))
+    with ctx.Pool(n_proc, initializer=_ref_init) as pool:
         def step():
-            return sum(pool.map(_cpu_worker, [(42, c) for c in chunks]))
+            return sum(pool.map(_ref_task, tasks, chunksize=1))
         for _ in range(max(args.warmup, 1)):
             step()
         t0 = time.perf_counter()
@@ -248,14 +271,15 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     value = per_step_cells * args.steps / dt
     sample = (f"each step = {len(pairs_per_step)} of {N_MODELS * N_ACC} (model, accelerator) pairs x all 256x64 cells "
-              f"= {per_step_cells} cells, spread over {len(chunks)} worker processes on {cores} usable cores; "
+              f"= {per_step_cells} cells in tasks of {task_cells}, pulled by {n_proc} worker processes on {cores} usable "
+              f"logical CPUs; "
               f"C restatement of the Go reference "
               f"(the Go path itself is single-goroutine and cannot be built here: no Go toolchain)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "processes": len(chunks), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "processes": n_proc, "kind": "port",
                          "sample": sample, **host_info(), "one_core_value": one["value"],
                          "parallel_speedup": value / one["value"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
