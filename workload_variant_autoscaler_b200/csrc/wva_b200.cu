@@ -481,6 +481,18 @@ int run_size_rounds(wva_handle* h, const SizeArgs& sa, int n) {
     const int D = size_depth_for(n);
     int size_rev = 1;  // solver returns to the block vote after a per-step excursion (0 = stays on the per-step path)
     if (const char* e = getenv("WVA_SIZE_REV")) size_rev = atoi(e);
+    // blocks of sz2_solve per SM (register limit: 4).  Fewer co-resident warps = a larger share of the sub-partition's
+    // FP64 pipe for each, i.e. a shorter critical path for the rounds that are as long as their longest chains;
+    // unused dynamic shared memory is what limits the residency.
+    int solve_bpsm = 4;
+    if (const char* e = getenv("WVA_SIZE_BLOCKS_PER_SM")) solve_bpsm = std::min(std::max(atoi(e), 1), 4);
+    size_t solve_pad = 0;
+    if (solve_bpsm < 4) {
+        solve_pad = (size_t)(227 * 1024) / (size_t)solve_bpsm - 2048;
+        solve_pad = solve_pad / 1024 * 1024;
+        CK(cudaFuncSetAttribute(sz2_solve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_pad));
+        CK(cudaFuncSetAttribute(sz2_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_pad));
+    }
     int dbg_round = -1;  // diagnostics: record per-request SM cycles of this round's sz2_solve (wva_dbg_read_size)
     if (const char* e = getenv("WVA_SIZE_DBG_ROUND")) dbg_round = atoi(e);
     const size_t per_cand = 2 * ((size_t)(1 << D) - 1 + 2);  // two searches: a tree each, plus the two end points
@@ -562,8 +574,8 @@ int run_size_rounds(wva_handle* h, const SizeArgs& sa, int n) {
                 g.dbg = (unsigned*)h->d_dbg.p;
                 h->dbg_n = cap;
             }
-            if (size_rev) sz2_solve<1><<<solve_blocks, 256, 0, h->stream>>>(g);
-            else sz2_solve<0><<<solve_blocks, 256, 0, h->stream>>>(g);
+            if (size_rev) sz2_solve<1><<<solve_blocks, 256, solve_pad, h->stream>>>(g);
+            else sz2_solve<0><<<solve_blocks, 256, solve_pad, h->stream>>>(g);
             h->launches += 6;
         }
         // candidates still unfinished after the group's last advance decide whether another group is needed
