@@ -287,7 +287,7 @@ __device__ __forceinline__ void dev_cp_async16(void* smem_dst, const void* gmem_
 }
 constexpr int kStagedFirst = 64;   // entries in the first staged window
 constexpr int kStagedSlots = 96;   // window slots of tbuf: pass 2 may index up to (hmax - 1) + 31 <= 94 when it re-uses the window
-constexpr int kStagedTbufD = kStagedSlots * 4 + 96;  // doubles per warp: the window, then the lanes' tail entries [3][32]
+constexpr int kStagedTbufD = kStagedSlots * 4 + 128;  // doubles per warp: the window, then one 32-byte tail entry per lane
 template <int STASH, int PF = 10, bool STAGED = false, int REV = 1>
 __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st,
                                            double* __restrict__ stash, double* __restrict__ tbuf = nullptr) {
@@ -306,14 +306,17 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     // The tail entry servRate[N-1] is needed wherever a loop hands over to the next one.  Holding it in registers
     // for the whole solve cost the pure-tail loops six registers and ptxas a worse schedule (54.7 instead of 42.5
     // cycles per state, measured); re-loading it from the table at every hand-over was one of the dependent trips
-    // to L2 this version removes.  So a staged solve parks it in shared memory (tsave[3][32], one column per lane)
-    // and WVA_LOAD_TAIL brings it back with three LDS; a solve that is not staged reads the table as before.
-    double* const tsave = STAGED ? tbuf + kStagedSlots * 4 + (threadIdx.x & 31) : nullptr;
+    // to L2 this version removes.  So a staged solve parks it in shared memory — one 32-byte slot per lane in the
+    // window's own entry format, so that a head group in which some lanes are already past their head selects the
+    // ADDRESS it reads (window slot or own tail slot) instead of selecting three doubles — and WVA_LOAD_TAIL brings
+    // it back with two LDS; a solve that is not staged reads the table as before.
+    double4* const tsave4 = STAGED ? reinterpret_cast<double4*>(tbuf + kStagedSlots * 4) + (threadIdx.x & 31) : nullptr;
 #define WVA_LOAD_TAIL(R)                                                    \
     if (STAGED && staged) {                                                 \
-        (R).b = tsave[0];                                                   \
-        (R).yh = tsave[32];                                                 \
-        (R).yl = tsave[64];                                                 \
+        const double4 t4_ = *tsave4;                                        \
+        (R).b = t4_.x;                                                      \
+        (R).yh = t4_.y;                                                     \
+        (R).yl = t4_.z;                                                     \
     } else {                                                                \
         load_recip(tab, nh, R);                                             \
     }
@@ -342,9 +345,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     const double tail_b = B.b;
     st.tail_rate = (float)tail_b;
     if (STAGED && staged) {
-        tsave[0] = B.b;
-        tsave[32] = B.yh;
-        tsave[64] = B.yl;
+        *tsave4 = make_double4(B.b, B.yh, B.yl, 0.0);
     }
     bool bail = !in_window(lam, kHiRateLo, kHiRateHi) || !in_window(tail_b, kHiRateLo, kHiRateHi) ||
                 !in_window(A.b, kHiRateLo, kHiRateHi);
@@ -406,22 +407,13 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             double4* tb = reinterpret_cast<double4*>(tbuf);
             const int lane = threadIdx.x & 31;
             bool ok = true;
-            Recip T;
-            WVA_LOAD_TAIL(T)
 #define WVA_SP1_GROUP(SEL, ST)                                                                                    \
     _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                               \
-        const double4 e = tb[k + u];                                                                              \
+        const double4 e = *((SEL) && !(n < nh) ? (const double4*)tsave4 : (const double4*)(tb + (k + u)));       \
         Recip R;                                                                                                  \
-        if (SEL) {                                                                                                \
-            const bool hd = n < nh;                                                                               \
-            R.b = hd ? e.x : T.b;                                                                                 \
-            R.yh = hd ? e.y : T.yh;                                                                               \
-            R.yl = hd ? e.z : T.yl;                                                                               \
-        } else {                                                                                                  \
-            R.b = e.x;                                                                                            \
-            R.yh = e.y;                                                                                           \
-            R.yl = e.z;                                                                                           \
-        }                                                                                                         \
+        R.b = e.x;                                                                                                \
+        R.yh = e.y;                                                                                               \
+        R.yl = e.z;                                                                                               \
         p = div_recip(__dmul_rn(p, lam), R);                                                                      \
         sum = __dadd_rn(sum, p);                                                                                  \
         if (ST && n < STASH) stash[n * 32] = p;                                                                   \
@@ -618,25 +610,16 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             double4* tb = reinterpret_cast<double4*>(tbuf);
             const int lane = threadIdx.x & 31;
             bool ok = true;
-            Recip T;
-            WVA_LOAD_TAIL(T)
             // when the whole head fits in the first window of pass 1 (entry e in slot e - 1) it is still there
             const bool reuse = hmax <= kStagedFirst;
             const double4* tbp = tb;
 #define WVA_SP2_GROUP(SEL)                                                                                        \
     _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                               \
-        const double4 e = tbp[k + u];                                                                             \
+        const double4 e = *((SEL) && !(i < nh) ? (const double4*)tsave4 : (const double4*)(tbp + (k + u)));      \
         Recip R;                                                                                                  \
-        if (SEL) {                                                                                                \
-            const bool hd = i < nh;                                                                               \
-            R.b = hd ? e.x : T.b;                                                                                 \
-            R.yh = hd ? e.y : T.yh;                                                                               \
-            R.yl = hd ? e.z : T.yl;                                                                               \
-        } else {                                                                                                  \
-            R.b = e.x;                                                                                            \
-            R.yh = e.y;                                                                                           \
-            R.yl = e.z;                                                                                           \
-        }                                                                                                         \
+        R.b = e.x;                                                                                                \
+        R.yh = e.y;                                                                                               \
+        R.yl = e.z;                                                                                               \
         const double a_ = __dmul_rn(p, lam);                                                                      \
         pn = div_recip(p, z);                                                                                     \
         p = div_recip(a_, R);                                                                                     \
