@@ -816,7 +816,10 @@ __global__ void __launch_bounds__(kSortThreads, 2) grid_sort_local(GridArgs g) {
 // Global order of the warp items by class (longest first): class cursors from the global
 // histogram, then a multi-CTA scatter with warp-aggregated atomics.
 // grid_kernel's CTA shape (the kernel is further down; grid_items_plan plans its queues)
-constexpr int kGkWarps = 16;    // 4 per sub-partition; 128 registers per thread keep the two FP64 chains of pass 2 apart
+#ifndef WVA_GK_WARPS
+#define WVA_GK_WARPS 16
+#endif
+constexpr int kGkWarps = WVA_GK_WARPS;    // 4 per sub-partition; 128 registers per thread keep the two FP64 chains of pass 2 apart
 constexpr int kGkThreads = kGkWarps * 32;
 constexpr int kGkTabWin = 32;  // table entries staged per warp (solve_shared_t STAGED)
 constexpr int kGkLong = -1;    // long-item warps per CTA: automatic     // long-item warps per SM (sub-partition 0)
@@ -886,7 +889,7 @@ __device__ __forceinline__ void grid_items_plan(const GridArgs& g) {
         const float long_work = wrk[k] + (float)(nl - cnt[k]) * item_us(k);
         int c_max = 0;
         while (c_max < kClasses - 1 && cnt[c_max + 1] == 0) ++c_max;  // longest class present
-        const float workers = (float)(kGkWarps * g.n_ctas) - 4.0f * (float)ctas;
+        const float workers = (float)(kGkWarps * g.n_ctas) - (float)(kGkWarps / 4) * (float)ctas;
         const float t_short = (wrk[kClasses] - long_work) / fmaxf(workers, 1.0f);
         const float t_long = nl ? slow[c] * long_us(c_max) : 0.0f;
         t_of[c] = fmaxf(t_short, t_long);
