@@ -191,6 +191,21 @@ def _ref_task(task):
     return c1 - c0
 
 
+def cpu_quota_cores():
+    """CPU time the cgroup grants, in cores (cgroup v2 cpu.max / v1 cfs quota), or None when unlimited / unknown."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
 def sample_pairs(n_pairs: int):
     total = N_MODELS * N_ACC
     n_pairs = max(1, min(n_pairs, total))
@@ -248,27 +263,34 @@ def run_reference(args):
     import oracle
     oracle.build()
     cores = len(os.sched_getaffinity(0))  # every logical CPU the process may use
-    # a step = a bounded sample of the workload: 2 x cores (model, accelerator) pairs (all 256 x 64 cells of each),
-    # cut into tasks of 2048 cells that the workers pull one at a time (the cost of a cell varies 100x with the
-    # pair and the rate: static chunks left most workers waiting for the slowest pair)
-    pairs_per_step = sample_pairs(min(max(2 * cores, 16), N_MODELS * N_ACC))
+    quota = cpu_quota_cores()            # ... unless a cgroup quota caps the CPU time below that
     per_pair = N_BATCH * N_REPLICAS
     task_cells = 2048
-    tasks = [(p, c0, min(c0 + task_cells, per_pair)) for p in pairs_per_step for c0 in range(0, per_pair, task_cells)]
-    per_step_cells = len(pairs_per_step) * per_pair
     # one-core rate on a small sample, so that the record shows what the process pool actually gained
     one = cpu_baseline_port(4, reps=3)
     ctx = mp.get_context("fork")
-    n_proc = min(cores, len(tasks))
+    n_proc = cores
     with ctx.Pool(n_proc, initializer=_ref_init) as pool:
-        def step():
-            return sum(pool.map(_ref_task, tasks, chunksize=1))
+        def run(pairs):
+            # tasks of 2048 cells that the workers pull one at a time (the cost of a cell varies 100x with the pair
+            # and the rate: static chunks left most workers waiting for the slowest pair)
+            tasks = [(p, c0, min(c0 + task_cells, per_pair)) for p in pairs for c0 in range(0, per_pair, task_cells)]
+            t0 = time.perf_counter()
+            n = sum(pool.map(_ref_task, tasks, chunksize=1))
+            return n, time.perf_counter() - t0
+        # a step = a bounded sample of the workload: evenly spaced (model, accelerator) pairs, all 256 x 64 cells of
+        # each; the sample is sized from a calibration pass so that the whole run takes about 90 s on this host
+        n_cal, t_cal = run(sample_pairs(min(max(cores // 2, 8), N_MODELS * N_ACC)))
+        rate = n_cal / t_cal
+        budget_s = 90.0 / (args.steps + max(args.warmup, 1))
+        n_pairs = int(min(max(rate * budget_s / per_pair, 8), N_MODELS * N_ACC))
+        pairs_per_step = sample_pairs(n_pairs)
+        per_step_cells = len(pairs_per_step) * per_pair
         for _ in range(max(args.warmup, 1)):
-            step()
-        t0 = time.perf_counter()
+            run(pairs_per_step)
+        dt = 0.0
         for _ in range(args.steps):
-            step()
-        dt = time.perf_counter() - t0
+            dt += run(pairs_per_step)[1]
     value = per_step_cells * args.steps / dt
     sample = (f"each step = {len(pairs_per_step)} of {N_MODELS * N_ACC} (model, accelerator) pairs x all 256x64 cells "
               f"= {per_step_cells} cells in tasks of {task_cells}, pulled by {n_proc} worker processes on {cores} usable "
@@ -279,7 +301,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "processes": n_proc, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "processes": n_proc, "cpu_quota_cores": quota, "kind": "port",
                          "sample": sample, **host_info(), "one_core_value": one["value"],
                          "parallel_speedup": value / one["value"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
