@@ -614,8 +614,24 @@ def run_ours(args):
 
     # a step is < 1 ms: keep the same load running before the timed region so that the 100 ms nvidia-smi samples
     # are taken under this workload (they continue through the timed region); fixed step count on every rank
+    def block_ms():
+        t = torch.tensor([sum(run_steps(100))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the same number on every rank: identical decisions below
+        return float(t.item())
+    prev = None
     for _ in range(PRE_ROLL_STEPS // 100):
-        run_steps(100)
+        prev = block_ms()
+    # ... and until the box has settled: two consecutive 100-step blocks within 2 % (a run started right after another
+    # job on the same GPUs was once 6 % slow for its whole timed region); bounded, and decided on the all-reduced
+    # time, so every rank runs the same number of blocks
+    settle_blocks = 0
+    for _ in range(60):
+        cur = block_ms()
+        settle_blocks += 1
+        if abs(cur - prev) <= 0.02 * prev:
+            break
+        prev = cur
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -717,6 +733,7 @@ def run_ours(args):
             "config": config_dict(world),
             "exchange": exchange, "gather_check_equal_local": gather_check,
             "exchange_overlapped_with_next_step": bool(overlap),
+            "pre_roll_steps": PRE_ROLL_STEPS + 100 * settle_blocks,
             "e2e": {"value": n_cells * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h),
                     "note": "wva_grid_solve through the C ABI with host buffers: H2D of the fleet (staged through the "
