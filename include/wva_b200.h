@@ -284,6 +284,7 @@ int wva_summarize(wva_handle *h, wva_summary *out);
  * binary-powering algorithm (integer exponents only occur) so that host oracle and device agree bit for bit; it is
  * not pinned against the Go binary (no Go toolchain here), see DESIGN.md.
  * Columns have n entries (host pointers, any may be NULL); entries of an invalid triple are 0 except rho.
+ * K < 0 is WVA_ERR_BAD_ARG (NewMM1KModel returns nil), K > 2^20 WVA_ERR_UNSUPPORTED.
  */
 typedef struct wva_mm1k_out {
     uint8_t *is_valid;

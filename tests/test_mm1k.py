@@ -85,7 +85,9 @@ def test_mm1k_device_function_bit_exact(engine, oracle_mod):
 
 
 @pytest.mark.gpu
-def test_mm1k_rejects_negative_K(engine):
+def test_mm1k_rejects_negative_and_oversized_K(engine):
     from workload_variant_autoscaler_b200 import WvaError
     with pytest.raises(WvaError):
         engine.mm1k_solve([-1], [1.0], [2.0])
+    with pytest.raises(WvaError):
+        engine.mm1k_solve([(1 << 20) + 1], [1.0], [2.0])

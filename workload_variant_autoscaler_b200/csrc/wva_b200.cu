@@ -1680,6 +1680,8 @@ int wva_mm1k_solve(wva_handle* h, int32_t n, const int32_t* K, const float* lamb
     if (n == 0) return WVA_OK;
     for (int i = 0; i < n; ++i)
         if (K[i] < 0) return h->fail(WVA_ERR_BAD_ARG, "MM1K: negative K");  // NewMM1KModel returns nil (mm1kmodel.go:20-22)
+    for (int i = 0; i < n; ++i)  // one thread walks the K + 1 states of a triple: bound the launch
+        if (K[i] > (1 << 20)) return h->fail(WVA_ERR_UNSUPPORTED, "MM1K: K above 2^20");
     CK(cudaSetDevice(h->device));
     const size_t N = (size_t)n;
     size_t o = 0;
