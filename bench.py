@@ -57,6 +57,8 @@ def parse_args():
                     help="(model, accelerator) pairs (16384 cells each) per repetition of cpu_baseline (5 repetitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary BASELINE configurations")
+    ap.add_argument("--ref-seconds", type=float, default=90.0,
+                    help="--impl reference: the per-step sample is sized so that the whole run takes about this long")
     return ap.parse_args()
 
 
@@ -279,10 +281,10 @@ def run_reference(args):
             n = sum(pool.map(_ref_task, tasks, chunksize=1))
             return n, time.perf_counter() - t0
         # a step = a bounded sample of the workload: evenly spaced (model, accelerator) pairs, all 256 x 64 cells of
-        # each; the sample is sized from a calibration pass so that the whole run takes about 90 s on this host
+        # each; the sample is sized from a calibration pass so that the whole run takes about --ref-seconds on this host
         n_cal, t_cal = run(sample_pairs(min(max(cores // 2, 8), N_MODELS * N_ACC)))
         rate = n_cal / t_cal
-        budget_s = 90.0 / (args.steps + max(args.warmup, 1))
+        budget_s = args.ref_seconds / (args.steps + max(args.warmup, 1))
         n_pairs = int(min(max(rate * budget_s / per_pair, 8), N_MODELS * N_ACC))
         pairs_per_step = sample_pairs(n_pairs)
         per_step_cells = len(pairs_per_step) * per_pair
