@@ -156,3 +156,65 @@ def test_reference_resource_exhaustion(oracle_mod):
     served = int(sum(1 for s in range(5) if win["feasible"][s] and win["replicas"][s] > 0))
     assert 0 < served < 5
     assert (used_units(f, win) <= f.type_capacity).all()
+
+
+# ---- the reference's SolveGreedy scenarios (greedy_test.go:410-977), same fixture, same servers -----------------
+def _srv_min(name, model, cls, rate, intok, outtok, maxb, min_rep):
+    s = _srv(name, model, cls, rate, intok, outtok, maxb)
+    s["minNumReplicas"] = min_rep
+    return s
+
+
+_SCENARIOS = {
+    # greedy_test.go:410-483
+    "PriorityExhaustive": ("PriorityExhaustive", [("server1", "llama-7b", "high-priority", 10, 100, 200, 16, 1),
+                                                   ("server2", "llama-7b", "high-priority", 10, 100, 200, 16, 1)]),
+    # :485-572
+    "PriorityRoundRobin": ("PriorityRoundRobin", [("server1", "llama-7b", "high-priority", 10, 100, 200, 16, 1),
+                                                   ("server2", "llama-7b", "high-priority", 10, 100, 200, 16, 1),
+                                                   ("server3", "llama-7b", "medium-priority", 10, 100, 200, 16, 1)]),
+    # :574-661
+    "RoundRobin": ("RoundRobin", [("server1", "llama-7b", "high-priority", 10, 100, 200, 16, 1),
+                                   ("server2", "llama-7b", "medium-priority", 10, 100, 200, 16, 1),
+                                   ("server3", "llama-7b", "low-priority", 10, 100, 200, 16, 1)]),
+    # :732-826
+    "HighLoadScenario": ("PriorityExhaustive", [("server1", "llama-7b", "high-priority", 100, 200, 300, 32, 2),
+                                                 ("server2", "llama-7b", "medium-priority", 80, 150, 250, 16, 1),
+                                                 ("server3", "llama-13b", "low-priority", 50, 200, 400, 8, 1)]),
+    # :828-901
+    "MixedModelTypes": ("RoundRobin", [("llama7b-server", "llama-7b", "high-priority", 40, 100, 200, 16, 1),
+                                        ("llama13b-server", "llama-13b", "high-priority", 30, 150, 300, 8, 1)]),
+    # :903-977
+    "EdgeCases": ("PriorityRoundRobin", [("zero-load-server", "llama-7b", "high-priority", 0, 100, 200, 16, 1),
+                                          ("high-load-server", "llama-7b", "medium-priority", 1000, 500, 1000, 64, 3)]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_SCENARIOS))
+def test_reference_greedy_scenarios(oracle_mod, name):
+    """Each scenario of the reference asserts only that somebody is served; here additionally: capacity holds and
+    the product's host pass (wva_solve_greedy) reproduces the oracle's solution from the same candidate table."""
+    from workload_variant_autoscaler_b200 import Allocs, Fleet, greedy_solve
+    from workload_variant_autoscaler_b200._abi import ALLOC_COLUMNS
+    policy, servers = _SCENARIOS[name]
+    # the fixture's own targets for (high-priority, llama-7b) (greedy_test.go:100-118: ITL 400, TTFT 20, TPS 15) and
+    # the lenient ones BasicAllocation swaps in
+    for hp in ((400, 20, 15), (100, 1000, 50)):
+        f = Fleet.from_spec(_ref_spec([_srv_min(*s) for s in servers], policy=policy, delayed=True, hp_7b=hp))
+        cand0 = oracle_mod.calculate(f)
+        cand_o, win_o = oracle_mod.solve(f, cand0.copy())
+        assert (used_units(f, win_o) <= f.type_capacity).all()
+        cand = Allocs(f.n_servers * f.n_acc)
+        for col, _ in ALLOC_COLUMNS:
+            getattr(cand, col)[:] = cand0.reshape(-1)[col]
+        cand_g, win_g = greedy_solve(f, cand)
+        assert_allocs_equal(win_g, win_o, f"{name}: winners")
+        assert_allocs_equal(cand_g, cand_o, f"{name}: candidates after best-effort scaling")
+        assert int(win_o["feasible"].sum()) >= 1, "the reference asserts that at least one server is served"
+
+
+def test_reference_greedy_no_servers(oracle_mod):  # greedy_test.go:237-250
+    from workload_variant_autoscaler_b200 import Fleet
+    f = Fleet.from_spec(_ref_spec([]))
+    cand, win = oracle_mod.solve(f)
+    assert win.size == 0
