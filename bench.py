@@ -271,7 +271,8 @@ def run_reference(args):
     # one-core rate on a small sample, so that the record shows what the process pool actually gained
     one = cpu_baseline_port(4, reps=3)
     ctx = mp.get_context("fork")
-    n_proc = cores
+    # one worker per CPU the process can actually get: 128 workers on a 16-core quota only add context switches
+    n_proc = cores if not quota else max(1, min(cores, int(round(quota))))
     with ctx.Pool(n_proc, initializer=_ref_init) as pool:
         def run(pairs):
             # tasks of 2048 cells that the workers pull one at a time (the cost of a cell varies 100x with the pair
