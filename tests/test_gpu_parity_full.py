@@ -5,7 +5,8 @@ oracle spread over the box's host cores by a process pool (it is single-threaded
  * configs[2]: latency sweep with N in {256, 512}, 256 rates, 64 pairs
  * configs[3]: size path on 512 servers x 8 accelerators with N up to 512
  * configs[4]: streaming, 32 ticks with arrival churn and token-statistics changes
- * multi-GPU: the peer-memory exchange kernel against NCCL (needs >= 2 GPUs on the box)
+ * multi-GPU (needs >= 2 GPUs on the box): the peer-memory exchange kernel against NCCL; the sharded solves
+   (unlimited and limited mode) under NCCL against the oracle on the whole fleet
 """
 import multiprocessing as mp
 import os
@@ -207,5 +208,61 @@ def test_peer_exchange_matches_nccl(tmp_path):
     import torch.multiprocessing as tmp_mp
     world = 2
     tmp_mp.spawn(_peer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(tmp_path, f"rank{r}.txt")).read() == "ok"
+
+
+# ---- multi-GPU: the product's sharded solves (unlimited and limited mode) against the oracle on the whole fleet --------
+def _sharded_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import datetime
+
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from workload_variant_autoscaler_b200 import Engine
+    from workload_variant_autoscaler_b200._abi import SAT_PRIORITY_ROUND_ROBIN
+    from workload_variant_autoscaler_b200.parallel import solve_sharded, solve_sharded_limited, torch_all_gather
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=120))
+    eng = Engine(rank)
+    ag = torch_all_gather(device=dev)
+    msg = "ok"
+    try:
+        # unlimited mode: shards solve independently, one all-gather of the winner records
+        f = synth_fleet(203, 4, seed=31, max_batch_choices=(4, 8, 16, 32, 64), zero_load_frac=0.1)
+        win = solve_sharded(lambda sh: eng.solve(sh)[1], f, rank=rank, world=world, all_gather=ag)
+        _, win_o = oracle.solve(f)
+        assert_allocs_equal(win, win_o, f"rank {rank}: sharded unlimited winners")
+        # limited mode: shards size their candidates, one all-gather of the tables, the same greedy pass on every rank
+        g = synth_fleet(61, 3, seed=32, max_batch_choices=(2, 4, 8, 16), zero_load_frac=0.1)
+        g.unlimited = False
+        g.saturation_policy = SAT_PRIORITY_ROUND_ROBIN
+        g.delayed_best_effort = True
+        g.type_capacity[:] = 30
+        g.srv_priority[:] = np.random.default_rng(3).choice([1, 5, 10], g.n_servers)
+        cand, win = solve_sharded_limited(lambda sh: eng.analyze(sh), g, rank=rank, world=world, all_gather=ag)
+        cand_o, win_o = oracle.solve(g)
+        assert_allocs_equal(win, win_o, f"rank {rank}: sharded limited winners")
+        assert_allocs_equal(cand, cand_o, f"rank {rank}: sharded limited candidates")
+    except AssertionError as exc:
+        msg = str(exc)[:500]
+    open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write(msg)
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_sharded_solves_on_two_gpus_match_the_oracle(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one box (gpurun --gpus 2)")
+    import torch.multiprocessing as tmp_mp
+    world = 2
+    tmp_mp.spawn(_sharded_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(tmp_path, f"rank{r}.txt")).read() == "ok"
