@@ -10,7 +10,10 @@ from workload_variant_autoscaler_b200 import Engine, synth_fleet  # noqa: E402
 
 e = Engine(0)
 L = e._L
-f = synth_fleet(12500, 8, seed=45, max_batch_choices=(4, 8, 16, 32, 64, 128, 256))
+if os.environ.get("SIZE_DBG_FLEET") == "config3":  # 80 k candidates, N <= 512
+    f = synth_fleet(10000, 8, seed=44, max_batch_choices=(4, 8, 16, 32, 64, 128, 256, 512))
+else:
+    f = synth_fleet(12500, 8, seed=45, max_batch_choices=(4, 8, 16, 32, 64, 128, 256))
 e.upload(f)
 e.resolve()
 L.wva_dbg_read_size.restype = C.c_longlong
@@ -30,8 +33,8 @@ for rnd in [int(x) for x in (sys.argv[1:] or ["0", "5", "14"])]:
     wmax = np.maximum.reduceat(cyc[order], first)
     print("warps", ws.size, "warp cycles: sum %.3e mean %.0f p50 %.0f p99 %.0f max %d" %
           (wmax.sum(dtype=np.float64), wmax.mean(), np.percentile(wmax, 50), np.percentile(wmax, 99), wmax.max()))
-    print("ideal us if packed on 148 SMs x 16 warps: %.1f;  longest warp alone: %.1f us" %
-          (wmax.sum(dtype=np.float64) / (148 * 16) / 1.965e3, wmax.max() / 1.965e3))
+    print("sum of warp cycles / (148 SMs x 32 warps): %.1f us;  longest warp: %.1f us;  warps above 80 %% of it: %d" %
+          (wmax.sum(dtype=np.float64) / (148 * 32) / 1.965e3, wmax.max() / 1.965e3, int((wmax > 0.8 * wmax.max()).sum())))
     for k in np.argsort(wmax)[::-1][:4]:
         sel = order[first[k]: first[k] + 32]
         sel = sel[w[sel] == ws[k]]

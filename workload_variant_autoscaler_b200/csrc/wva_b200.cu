@@ -1855,10 +1855,10 @@ __global__ void div_selfcheck_kernel(unsigned long long seed, int iters, unsigne
         }
         const long long eb = (long long)((r2 >> 8) % 121) - 60;
         const double b = __longlong_as_double((long long)(((unsigned long long)(1023 + eb) << 52) | mb));
-        // dividend: random mantissa (sometimes all ones), exponent in [-340, 660] (p * lambda)
+        // dividend: random mantissa (sometimes all ones), exponent in [-340, 940] (p * lambda)
         unsigned long long ma = r1 & 0x000FFFFFFFFFFFFFull;
         if (((r2 >> 20) & 7) == 0) ma = 0x000FFFFFFFFFFFFFull - (r1 & 0xf);
-        const long long ea = (long long)((r2 >> 24) % 1001) - 340;
+        const long long ea = (long long)((r2 >> 24) % 1281) - 340;
         const double a = __longlong_as_double((long long)(((unsigned long long)(1023 + ea) << 52) | ma));
         const Recip rc = make_recip(b);
         const double q = div_recip(a, rc), want = __ddiv_rn(a, b);
@@ -1868,11 +1868,11 @@ __global__ void div_selfcheck_kernel(unsigned long long seed, int iters, unsigne
         z.yl = __dmul_rn(__fma_rn(-b, rc.yh, 1.0), rc.yh);
         const double q2 = div_recip(a, z);
         if (__double_as_longlong(q2) != __double_as_longlong(want)) ++bad;
-        // the tail step with the pre-multiplied low word (step_recip): p in [2^-280, 2^600), float32 lambda in
+        // the tail step with the pre-multiplied low word (step_recip): p in [2^-280, 2^880), float32 lambda in
         // [2^-60, 2^60]
         {
             const unsigned long long r3 = next();
-            const long long ep = (long long)(r3 % 881) - 280;
+            const long long ep = (long long)(r3 % 1160) - 280;
             const double pp = __longlong_as_double((long long)(((unsigned long long)(1023 + ep) << 52) | ma));
             const long long el = (long long)((r3 >> 12) % 121) - 60;
             const double lam = __longlong_as_double(
@@ -1880,6 +1880,21 @@ __global__ void div_selfcheck_kernel(unsigned long long seed, int iters, unsigne
             const double got = step_recip(pp, lam, __dmul_rn(lam, rc.yl), rc);
             const double want3 = __ddiv_rn(__dmul_rn(pp, lam), b);
             if (__double_as_longlong(got) != __double_as_longlong(want3)) ++bad;
+        }
+        // the division by the normalising sum: sum in [1, 2^900), p in [max(2^-280, sum * 2^-960), sum]
+        {
+            const unsigned long long r4 = next(), r5 = next();
+            const long long es = (long long)(r4 % 900);
+            const double S = __longlong_as_double((long long)(((unsigned long long)(1023 + es) << 52) | (r5 & 0x000FFFFFFFFFFFFFull)));
+            const long long lo = es - 959 > -280 ? es - 959 : -280;
+            const long long epp = lo + (long long)((r4 >> 16) % (unsigned long long)(es - lo + 1));
+            const double pp = __longlong_as_double((long long)(((unsigned long long)(1023 + epp) << 52) | mb));
+            Recip zz;
+            zz.b = S;
+            zz.yh = __ddiv_rn(1.0, S);
+            zz.yl = __dmul_rn(__fma_rn(-S, zz.yh, 1.0), zz.yh);
+            const double got = div_recip(pp, zz), want4 = __ddiv_rn(pp, S);
+            if (__double_as_longlong(got) != __double_as_longlong(want4)) ++bad;
         }
     }
     if (bad) atomicAdd(mismatches, bad);

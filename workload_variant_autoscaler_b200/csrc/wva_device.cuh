@@ -178,19 +178,25 @@ __device__ __forceinline__ double go_pow_uint(double x, long long n) {
     return go_ldexp(a1, ae);
 }
 
-// Exponent windows (high 32 bits of the double).  p in [2^-280, 2^600) keeps every
-// intermediate of both reciprocal divisions normal when lambda and the service rates
-// lie in [2^-60, 2^60] and the normalising sum is < 2^620 (derivation in DESIGN.md).
+// Exponent windows (high 32 bits of the double).  With lambda and the service rates in [2^-60, 2^60], p in
+// [2^-280, 2^880) keeps every intermediate of the step's reciprocal division normal (the largest is q0 < 2^1000) and
+// the normalising sum below 2^900; the division by the sum additionally needs p / sum >= 2^-960 (so that the low-word
+// product is either normal or negligible): pass 2 raises its lower bound to sum * 2^-960 when the sum is that large
+// (derivation in DESIGN.md).  Round 1 stopped at 2^600 / 2^620: chains of N = 512 near saturation peak above 2^600
+// and spent their tails outside the 16-step blocks.
 #define WVA_HI(e) ((unsigned)((1023 + (e)) << 20))
 __device__ __forceinline__ bool in_window(double p, unsigned lo, unsigned hi) {
     return ((unsigned)__double2hiint(p) - lo) < (hi - lo);
 }
 constexpr unsigned kHiPLo = WVA_HI(-280);
-constexpr unsigned kHiPHi = WVA_HI(600);
+constexpr int kPHiExp = 880, kPHiExpNarrow = 600;
+constexpr unsigned kHiPHi = WVA_HI(kPHiExp), kHiPHiNarrow = WVA_HI(kPHiExpNarrow);
+constexpr unsigned kHiPnSpan = (unsigned)(960 << 20);  // pass 2: p >= 2^(E(sum) - 960)
 constexpr unsigned kHiRateLo = WVA_HI(-60);
 constexpr unsigned kHiRateHi = WVA_HI(60);
 constexpr unsigned kHiSumLo = WVA_HI(0);
-constexpr unsigned kHiSumHi = WVA_HI(620);
+constexpr unsigned kHiSumHi = WVA_HI(900), kHiSumHiNarrow = WVA_HI(620);
+constexpr unsigned kHiRowSumHi = WVA_HI(620);  // solve_row shares a chain only below this (its pass 2 keeps the fixed window)
 
 // ---------------------------------------------------------------------------
 // MM1ModelStateDependent: pkg/analyzer/mm1modelstatedependent.go:38-116.
@@ -288,9 +294,15 @@ __device__ __forceinline__ void dev_cp_async16(void* smem_dst, const void* gmem_
 constexpr int kStagedFirst = 64;   // entries in the first staged window
 constexpr int kStagedSlots = 96;   // window slots of tbuf: pass 2 may index up to (hmax - 1) + 31 <= 94 when it re-uses the window
 constexpr int kStagedTbufD = kStagedSlots * 4 + 128;  // doubles per warp: the window, then one 32-byte tail entry per lane
-template <int STASH, int PF = 10, bool STAGED = false, int REV = 1>
+// WIDE: the windows of the comment above kHiPLo.  grid_kernel's instantiation (STAGED) keeps the round-1 windows
+// (2^600 / 2^620, fixed pass-2 bound): its batch sizes stay below what needs more, and the extra pass-2 set-up measurably
+// perturbed its register allocation (+1-2 %); everything else (size path, sweep, row solve callers) is WIDE.
+template <int STASH, int PF = 10, bool STAGED = false, int REV = 1, bool WIDE = !STAGED>
 __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N, int K, float lambda, ModelStats& st,
                                            double* __restrict__ stash, double* __restrict__ tbuf = nullptr) {
+    constexpr unsigned kHiPHi = WIDE ? wva::kHiPHi : kHiPHiNarrow;   // shadow the namespace constants
+    constexpr unsigned kHiSumHi = WIDE ? wva::kHiSumHi : kHiSumHiNarrow;
+    constexpr int kPHiExp = WIDE ? wva::kPHiExp : kPHiExpNarrow;
     const unsigned warp_mask = __activemask();
     const double lam = (double)lambda;
     const int nh = N - 1;
@@ -356,7 +368,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     const double p1 = p;
     unsigned thr_hi = 0;
     if (K < (1 << 23)) thr_hi = (unsigned)__double2hiint(__dmul_rn(fmin(1.0, p1), 0x1p-78));
-    // merged fast window [max(thr, 2^-280), 2^600): inside it the step is a plain reciprocal step
+    // merged fast window [max(thr, 2^-280), 2^880): inside it the step is a plain reciprocal step
     const unsigned lo_eff = thr_hi > kHiPLo ? thr_hi : kHiPLo;
     const unsigned span_eff = kHiPHi - lo_eff;
 
@@ -367,6 +379,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     // inside a block simply runs to the end of the block: those states add nothing.
     unsigned blk_lo = 1, blk_span = 0;  // empty window = blocks disabled
     unsigned blk16_lo = 1, blk16_span = 0;
+    int e_lo_w = 0;  // lower exponent bound of one step's factor (pass 2 re-derives its block windows from it)
     {
         const float smax = tab_prefix_max(tab, nh), smin = tab_suffix_min(tab, 0);
         if (!bail && smin > 0.0f && smax >= smin) {
@@ -374,14 +387,15 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
             const int El = (int)(__float_as_uint(lambda) >> 23), Ex = (int)(__float_as_uint(smax) >> 23),
                       En = (int)(__float_as_uint(smin) >> 23);
             const int e_lo = El - Ex - 1, e_hi = El - En + 1;
-            const int lo_exp = -279 - 3 * (e_lo < 0 ? e_lo : 0), hi_exp = 600 - 3 * (e_hi > 0 ? e_hi : 0);
+            e_lo_w = e_lo;
+            const int lo_exp = -279 - 3 * (e_lo < 0 ? e_lo : 0), hi_exp = kPHiExp - 3 * (e_hi > 0 ? e_hi : 0);
             if (lo_exp < hi_exp && lo_exp > -1000 && hi_exp > -1000) {
                 const unsigned lo4 = WVA_HI(lo_exp), hi4 = WVA_HI(hi_exp);
                 blk_lo = lo4 > lo_eff ? lo4 : lo_eff;
                 blk_span = hi4 > blk_lo ? hi4 - blk_lo : 0;
             }
             // the same for 16-step blocks (15 unchecked steps)
-            const int lo_exp16 = -279 - 15 * (e_lo < 0 ? e_lo : 0), hi_exp16 = 600 - 15 * (e_hi > 0 ? e_hi : 0);
+            const int lo_exp16 = -279 - 15 * (e_lo < 0 ? e_lo : 0), hi_exp16 = kPHiExp - 15 * (e_hi > 0 ? e_hi : 0);
             if (lo_exp16 < hi_exp16 && lo_exp16 > -1000 && hi_exp16 > -1000) {
                 const unsigned lo16 = WVA_HI(lo_exp16), hi16 = WVA_HI(hi_exp16);
                 blk16_lo = lo16 > lo_eff ? lo16 : lo_eff;
@@ -543,8 +557,27 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     z.yl = __dmul_rn(__fma_rn(-sum, z.yh, 1.0), z.yh);
     double acc = 0.0, sum_p = z.yh, pn = 0.0, di = 1.0, acc_at_N = 0.0;
     p = p1;
-    // pass 2 uses the same block window (its lower edge is >= 2^-279 / 2^(3 e_lo), all the division needs)
-    const unsigned blk2_lo = blk_lo, blk2_span = blk_span;
+    // pass 2 uses the same windows unless the sum is above 2^680: then the division by the sum needs
+    // p >= lo2 = 2^(E(sum) - 960), states below it take the exact IEEE path (p2_slow), and the block windows' lower
+    // edges move up with it (a block's unchecked steps may shrink p by 2^e_lo each)
+    const unsigned sum_hi_w = (unsigned)__double2hiint(sum);
+    const unsigned lo2 = (WIDE && sum_hi_w > kHiPLo + kHiPnSpan) ? sum_hi_w - kHiPnSpan : kHiPLo;
+    const unsigned span2 = kHiPHi - lo2;
+    unsigned blk2_lo = blk_lo, blk2_span = blk_span, blk16b_lo = blk16_lo, blk16b_span = blk16_span;
+    if (WIDE && lo2 > kHiPLo) {
+        const unsigned dn = e_lo_w < 0 ? (unsigned)(-e_lo_w) : 0u;
+        const unsigned lo4n = lo2 + ((3u * dn + 1u) << 20), lo16n = lo2 + ((15u * dn + 1u) << 20);
+        if (lo4n > blk2_lo) {
+            const unsigned hi4 = blk2_lo + blk2_span;
+            blk2_lo = lo4n;
+            blk2_span = hi4 > lo4n ? hi4 - lo4n : 0u;
+        }
+        if (lo16n > blk16b_lo) {
+            const unsigned hi16 = blk16b_lo + blk16b_span;
+            blk16b_lo = lo16n;
+            blk16b_span = hi16 > lo16n ? hi16 - lo16n : 0u;
+        }
+    }
     __syncwarp(warp_mask);
     {
         int i = 1;  // p holds p[i]
@@ -557,8 +590,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 const int i4 = i_st < N ? i_st : N;
                 while (i + 3 <= i4) {
                     const double q0 = stash[(i - 1) * 32], q1 = stash[i * 32], q2 = stash[(i + 1) * 32], q3 = stash[(i + 2) * 32];
-                    if (!(WVA_FASTWIN(q0, kHiPLo, kHiPHi - kHiPLo) && WVA_FASTWIN(q1, kHiPLo, kHiPHi - kHiPLo) &&
-                          WVA_FASTWIN(q2, kHiPLo, kHiPHi - kHiPLo) && WVA_FASTWIN(q3, kHiPLo, kHiPHi - kHiPLo)))
+                    if (!(WVA_FASTWIN(q0, lo2, span2) && WVA_FASTWIN(q1, lo2, span2) &&
+                          WVA_FASTWIN(q2, lo2, span2) && WVA_FASTWIN(q3, lo2, span2)))
                         break;
                     const double n0 = div_recip(q0, z), n1 = div_recip(q1, z), n2 = div_recip(q2, z), n3 = div_recip(q3, z);
                     acc = __dadd_rn(acc, __dmul_rn(di, n0));
@@ -582,7 +615,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
 #pragma unroll 2
             for (; i <= i_st; ++i) {
                 p = stash[(i - 1) * 32];
-                if (!WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) break;
+                if (!WVA_FASTWIN(p, lo2, span2)) break;
                 pn = div_recip(p, z);
                 acc = __dadd_rn(acc, __dmul_rn(di, pn));
                 di = __dadd_rn(di, 1.0);
@@ -599,7 +632,7 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 WVA_LOAD_TAIL(A)
                 if (i - 1 < nh) load_recip(tab, i - 1, A);
                 const double pprev = stash[(i - 2) * 32];
-                p = WVA_FASTWIN(pprev, kHiPLo, kHiPHi - kHiPLo) ? div_recip(__dmul_rn(pprev, lam), A)
+                p = WVA_FASTWIN(pprev, lo2, span2) ? div_recip(__dmul_rn(pprev, lam), A)
                                                                  : __ddiv_rn(__dmul_rn(pprev, lam), A.b);
             }
         }
@@ -685,8 +718,8 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
     }
             for (;;) {  // block phase, as in pass 1; pure-tail also needs i > N (sumP complete)
                 if (!(i + 16 <= j_end)) WVA_CNT(14);
-                if (!WVA_FASTWIN(p, blk16_lo, blk16_span)) WVA_CNT(15);
-                if (__all_sync(__activemask(), i > nh + 1 && i > N && i + 16 <= j_end && WVA_FASTWIN(p, blk16_lo, blk16_span))) {
+                if (!WVA_FASTWIN(p, blk16b_lo, blk16b_span)) WVA_CNT(15);
+                if (__all_sync(__activemask(), i > nh + 1 && i > N && i + 16 <= j_end && WVA_FASTWIN(p, blk16b_lo, blk16b_span))) {
                     WVA_CNT(10);
                     const double cA = __dmul_rn(lam, A.yl);
 #pragma unroll
@@ -711,11 +744,11 @@ __device__ __noinline__ int solve_shared_t(const double* __restrict__ tab, int N
                 break;
             }
             for (int rv = 0; REV == 0 || rv < REV; ++rv) {  // per-step phase (see pass 1)
-                if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) goto p2_slow;
+                if (i >= j_end || !WVA_FASTWIN(p, lo2, span2)) goto p2_slow;
                 if (i < nh) prefetch_l1(tab + 4 * (i + PF));
                 WVA_CNT(12);
                 WVA_P2_STEP(A)
-                if (i >= j_end || !WVA_FASTWIN(p, kHiPLo, kHiPHi - kHiPLo)) goto p2_slow;
+                if (i >= j_end || !WVA_FASTWIN(p, lo2, span2)) goto p2_slow;
                 WVA_P2_STEP(B)
             }
             continue;
@@ -803,7 +836,7 @@ __device__ __forceinline__ bool solve_row(const double* __restrict__ tab, int le
             const int El = (int)(__float_as_uint(lambda) >> 23), Ex = (int)(__float_as_uint(smax) >> 23),
                       En = (int)(__float_as_uint(smin) >> 23);
             const int e_lo = El - Ex - 1, e_hi = El - En + 1;
-            const int lo_exp = -279 - 3 * (e_lo < 0 ? e_lo : 0), hi_exp = 600 - 3 * (e_hi > 0 ? e_hi : 0);
+            const int lo_exp = -279 - 3 * (e_lo < 0 ? e_lo : 0), hi_exp = kPHiExp - 3 * (e_hi > 0 ? e_hi : 0);
             if (lo_exp < hi_exp && lo_exp > -1000 && hi_exp > -1000) {
                 const unsigned lo4 = WVA_HI(lo_exp), hi4 = WVA_HI(hi_exp);
                 blk_lo = lo4 > lo_eff ? lo4 : lo_eff;
@@ -837,7 +870,7 @@ __device__ __forceinline__ bool solve_row(const double* __restrict__ tab, int le
     const unsigned hp = (unsigned)__double2hiint(p);
     const bool negligible = hp < thr_hi && rate_below(lambda, tab_suffix_min(tab, n));
     if (!negligible && !(p == 0.0)) return false;
-    if (!in_window(sum, kHiSumLo, kHiSumHi)) return false;
+    if (!in_window(sum, kHiSumLo, kHiRowSumHi)) return false;  // above: no sharing, the cells take the full solver
     j_last = n;
     Recip z;
     z.b = sum;
